@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the SMC objective hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the forward particle filter (psvo_smc_forward: SVO.SMC + compute_log_ZSMC,
+src/SMC/SVO.py:60-180,302-311) over one batch of synthetic sequences, in production mode (in-kernel Philox).
+Workload `c5_shard` = BASELINE.json configs[4] (Dx=16, Dy=32, MLP width 256, n_particles=4096, T=1000) with the
+per-GPU share of the batch at 8 GPUs (B=128 per GPU; the full B=1024 needs 268 GB of particle output and does
+not fit one GPU).  Sequences are independent: rank r owns sequences [r*B, (r+1)*B) -- weak scaling, no data-path
+collective; at 8 GPUs the global batch is exactly the 1024 of configs[4].
+
+One JSON line on rank 0.  `value` = device-timed throughput with inputs resident in HBM; `e2e` = the same through
+the reference-facing call AESMC.get_log_ZSMC(obs) with obs in pinned HOST memory (H2D copy + D2H of log_ZSMC inside
+the timed region).  `roofline` is for the dominant kernel (smc_propagate), `cpu_baseline` is the oracle restatement
+(PyTorch CPU, not TensorFlow -- TF 1.12 cannot be installed here) timed on this box's host cores.
+`--impl reference` times that CPU restatement alone (all host threads) on a bounded sample of the same workload."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: per-GPU batch and shape.  cls: facade class used for the e2e call.
+    "c5_shard": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=4096, T=1000, B=128,
+                     note="BASELINE configs[4] (N=4096,T=1000,Dx=16,Dy=32,H=256), B=128 sequences per GPU (=1024/8)"),
+    "c3_lds": dict(cls="AESMC", Dx=4, Dy=4, H=[], N=1024, T=100, B=256,
+                   note="BASELINE configs[2] linear-Gaussian SSM, N=1024, B=256, T=100"),
+    "c1_fhn": dict(cls="AESMC", Dx=2, Dy=1, H=[32], N=64, T=200, B=1,
+                   note="BASELINE configs[0] FHN shape, N=64, T=200, B=1 (latency-bound single chain)"),
+    "c4_allen": dict(cls="AESMC", Dx=4, Dy=1, H=[64], N=2048, T=1000, B=1, poisson=True,
+                     note="BASELINE configs[3] shape, poisson emission, N=2048, T=1000, B=1"),
+    "tiny": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=512, T=20, B=8, note="smoke-size config-5 shape"),
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_flags(w):
+    from psvo_b200.flags import default_flags
+    hs = ",".join(str(h) for h in w["H"])
+    return default_flags(Dx=w["Dx"], Dy=w["Dy"], n_particles=w["N"], time=w["T"], batch_size=w["B"],
+                         q0_layers=hs, q1_layers=hs, q2_layers=hs, f_layers=hs, g_layers=hs,
+                         poisson_emission=bool(w.get("poisson", False)),
+                         PSVO=False, SVO=False, AESMC=True)
+
+
+def synth_obs(w, B, seed, first_seq):
+    """synthetic observations of the workload's shape; sequence b depends only on its global index"""
+    out = torch.empty(B, w["T"], w["Dy"])
+    for b in range(B):
+        g = torch.Generator().manual_seed(seed * 100003 + first_seq + b)
+        t = torch.arange(w["T"], dtype=torch.float32)[:, None]
+        ph = torch.rand(1, w["Dy"], generator=g) * 6.28
+        out[b] = torch.sin(0.05 * t + ph) + 0.1 * torch.randn(w["T"], w["Dy"], generator=g)
+    if w.get("poisson"):
+        out = torch.floor(out.abs() * 3)
+    return out
+
+
+def flops_per_particle_step(w):
+    dims_q1 = [w["Dx"]] + w["H"] + [w["Dx"]]
+    dims_g = [w["Dx"]] + w["H"] + [w["Dy"]]
+    f = 0
+    for d in (dims_q1, dims_g):
+        f += sum(2 * a * b for a, b in zip(d[:-1], d[1:]))
+    return f + 40 * w["Dx"] + 10 * w["Dy"]
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import ctypes as C
+    from psvo_b200 import _lib, functional as Fn
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.AESMC import AESMC
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, T, N, Dx = w["B"], w["T"], w["N"], w["Dx"]
+    FLAGS = make_flags(w)
+    torch.manual_seed(1234)
+    model = SSM(FLAGS).to(dev)
+    smc = AESMC(model, FLAGS)
+    obs_host = synth_obs(w, B, 1234, rank * B).pin_memory()
+    obs_dev = obs_host.to(dev)
+    P = model.dist_params()
+    flags = Fn.flag_bits(True, True, True, bool(w.get("poisson", False)))
+    bufs = {}
+
+    def step_resident(seed):
+        r = Fn.smc_forward_raw(P, flags, obs_dev, obs_dev, obs_dev[:, 0].contiguous(), N, seed=seed,
+                               seq_offset=rank * B, out=bufs)
+        bufs.update(r)
+        return r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    lib.psvo_profile_read(None, None)               # reset launch counters
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step_resident(100 + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = (C.c_int64 * 8)()
+    lib.psvo_profile_read(None, launches)
+    n_launch = int(sum(launches))
+
+    # ---- per-kernel durations (CUDA events on the launching stream, one extra step with the hooks on)
+    lib.psvo_profile_enable(1)
+    step_resident(999)
+    torch.cuda.synchronize()
+    kms, kl = (C.c_double * 8)(), (C.c_int64 * 8)()
+    lib.psvo_profile_read(kms, kl)
+    lib.psvo_profile_enable(0)
+
+    # ---- timed region 2: end to end through the reference-facing call, host buffers
+    e2e_ms = None
+    if not args.no_e2e:
+        def step_e2e():
+            o = obs_host.to(dev, non_blocking=True)                   # H2D of the step's input
+            log_ZSMC, _ = smc.get_log_ZSMC(o, None, out=bufs)
+            return float(log_ZSMC.detach().cpu())                     # D2H of the step's result
+        step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            val = step_e2e()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
+    logZ_mean = float(bufs["logZ_b"].mean())
+    if rank != 0:
+        return None
+
+    psteps = world * B * T * N
+    peaks, peak_src = read_peaks()
+    prop_ms_avg = kms[0] / max(kl[0], 1)
+    step_ms = ms / args.steps
+    flop_ps = flops_per_particle_step(w)
+    bytes_ps = 8 * Dx + 4                                             # write X_t, X_anc_t, log_W_t
+    fl_launch = flop_ps * B * N                                       # one propagate launch = one time step of the shard
+    by_launch = (4 * Dx + 4 + 4 * Dx) * B * N                         # propagate itself: read X_anc, write X_t, log_W
+    hbm_time = bytes_ps * B * N * T / (peaks["hbm_gbs"] * 1e9)
+    tensor_time = flop_ps * B * N * T / (peaks["bf16_tflops_sustained"] * 1e12)
+    bound = "tensor" if tensor_time > hbm_time else "hbm"
+    if bound == "tensor":
+        achieved = fl_launch / (prop_ms_avg * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None}
+    else:
+        achieved = by_launch / (prop_ms_avg * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+    roof.update({"kernel": "smc_propagate_kernel", "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
+                 "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
+                 "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,
+                 "kernel_share_of_step": {"smc_propagate": kms[0] / max(sum(kms), 1e-9), "smc_resample": kms[1] / max(sum(kms), 1e-9),
+                                          "mlp_rows": kms[2] / max(sum(kms), 1e-9)},
+                 "hbm_frac_whole_step": (bytes_ps * B * N * T / (step_ms * 1e-3) / 1e9) / peaks["hbm_gbs"]})
+    line = {
+        "metric": "particle-steps/sec (SMC forward filter)", "value": psteps / (step_ms * 1e-3), "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": w["note"], "class": w["cls"], "n_particles": N, "T": T,
+                   "batch_per_gpu": B, "global_batch": B * world, "Dx": Dx, "Dy": w["Dy"], "mlp_hidden": w["H"],
+                   "rng": "in-kernel Philox4x32-10", "parallelism": "sequence-sharded dp%d" % world,
+                   "l2": "outputs per step (%.1f GB) exceed L2; no flush needed" % ((8 * Dx + 8) * B * N * T / 1e9)},
+        "gpu_launches": n_launch, "clocks": clocks, "roofline": roof, "log_ZSMC": logZ_mean,
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": psteps / (e2e_ms / args.steps * 1e-3), "unit": "particle-steps/s",
+                       "h2d_bytes_per_step": obs_host.numel() * 4, "d2h_bytes_per_step": 4,
+                       "ms_per_step": e2e_ms / args.steps, "call": "psvo_b200.SMC.AESMC.get_log_ZSMC(obs)"}
+    return line
+
+
+def cpu_sample(w, budget_s=15.0, threads=None):
+    """Time the oracle restatement (PyTorch CPU fp32) on a bounded slice of the workload."""
+    from oracle import psvo_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    F = O.Flags(poisson_emission=bool(w.get("poisson", False)))
+    P = O.make_params(1234, w["Dx"], w["Dy"], w["Dy"], w["Dy"], w["H"], F)
+    N = w["N"]
+    Bs = min(w["B"], 8)
+
+    def run(Ts):
+        obs = synth_obs(w, Bs, 1234, 0)[:, :Ts]
+        g = torch.Generator().manual_seed(1)
+        eps = torch.randn(Bs, Ts, N, w["Dx"], generator=g)
+        u = torch.rand(Bs, Ts, N, generator=g)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.smc_forward(P, F, obs, obs, obs[:, 0], eps, u)
+        return time.perf_counter() - t0
+
+    Ts = min(w["T"], 4)
+    dt = run(Ts)                                         # warm-up + calibration
+    rate = Bs * Ts * N / dt
+    Ts = int(max(4, min(w["T"], budget_s * rate / (Bs * N))))
+    dt = run(Ts)
+    return {"value": Bs * Ts * N / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": "oracle/psvo_oracle.py smc_forward (PyTorch CPU fp32 restatement, not TensorFlow), B=%d, T=%d, N=%d "
+                      "slice of %s, %.1f s" % (Bs, Ts, N, w["note"], dt),
+            "published_reference": "TF 1.12 on an unnamed CPU box: ~14k particle-steps/s forward-only at N=16 "
+                                   "(notebooks/PSVO.ipynb, BASELINE.md)"}
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return None
+    vals = []
+    info = None
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_sample(w, budget_s=2.0)
+    for _ in range(args.steps):
+        info = cpu_sample(w, budget_s=max(3.0, 45.0 / args.steps))
+        vals.append(info["value"])
+    v = statistics.median(vals)
+    info["value"] = v
+    Bs = min(w["B"], 8)
+    return {"impl": "reference", "metric": "particle-steps/sec (SMC forward filter)", "value": v, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": w["note"], "sample": info["sample"]},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5_shard", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--T", type=int, default=None, help="override the number of time steps (debug)")
+    ap.add_argument("--B", type=int, default=None, help="override sequences per GPU (debug)")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.T:
+        w["T"] = args.T; w["note"] += " [T overridden to %d]" % args.T
+    if args.B:
+        w["B"] = args.B; w["note"] += " [B overridden to %d]" % args.B
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        line = run_reference(args, w, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_ours(args, w, rank, world, local_rank)
+        if rank == 0:
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_sample(w)
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,381 @@
+// smc_forward.cu -- forward particle filter: propagate + weight (K1) and normalise + resample + gather (K2).
+//
+// Reference: SVO.SMC (src/SMC/SVO.py:60-180), sample_from_2_dist diag branch (:182-197,228-232),
+// resample_X / get_resample_idx (:243-300), compute_log_ZSMC (:302-311).  SURVEY.md App. A.3-A.5.
+//
+// Per time step two kernels run back to back on the caller's stream:
+//   smc_propagate : grid over (sequence, particle tile).  One thread owns PPT particles: loads the resampled
+//                   parent X_anc[t-1], evaluates MLP q1 (and f), fuses with the per-sequence q2 mean, samples
+//                   X_t, evaluates MLP g and the three log densities, writes X_t and log_W_t.  Weights live in
+//                   shared memory and are read as warp broadcasts; nothing is exchanged between threads.
+//   smc_resample  : one CTA per sequence.  log-sum-exp of log_W_t, order-independent fixed-point CDF (integer
+//                   block scan), inverse-CDF binary search per child, ancestor gather X_anc[t] = X_t[a].
+// HBM layout is sequence-major (B,T,N,D): every (b,t) slab a kernel touches is contiguous.
+#include "mlp_tile.cuh"
+#include "smc_kernels.h"
+
+namespace psvo {
+
+// ------------------------------------------------------------------------------------------------------
+// K0: sigma block.  sig[slot*32 + d] = max(softplus(sigma_con[d]), sigma_min)  (1 where the dist has none)
+// ------------------------------------------------------------------------------------------------------
+__global__ void sigma_block_kernel(SigmaSrc src, float* __restrict__ sig) {
+  const int slot = blockIdx.x, d = threadIdx.x;
+  if (slot >= SIG_SLOTS || d >= 32) return;
+  float v = 1.0f;
+  if (src.con[slot] != nullptr && d < src.dim[slot]) v = sigma_from_con(src.con[slot][d], src.smin[slot]);
+  sig[slot * 32 + d] = v;
+}
+
+int launch_sigma_block(const SigmaSrc& src, float* sig, cudaStream_t st) {
+  ProfScope ps_(PK_SIGMA, st);
+  sigma_block_kernel<<<SIG_SLOTS, 32, 0, st>>>(src, sig);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1: propagate + weight
+// ------------------------------------------------------------------------------------------------------
+template <int DXP>
+struct StepConsts {        // per-CTA constants in shared memory
+  float s1[DXP];           // stddev of d1 (q0 at t = 0, q1 afterwards)
+  float sf[DXP];           // stddev used by f_lp
+  float sp[DXP];           // proposal stddev (fused or s1)
+  float inv1[DXP], inv2[DXP];
+  float sg[PSVO_MAX_DY];
+  float ld_p, ld_f, ld_g;  // sum log stddev
+};
+
+template <int DXP, int DYP, int PPT>
+__global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N;
+  const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP;
+  const bool poisson = a.flags & PSVO_F_POISSON;
+  const bool t0 = a.t == 0;
+  const bool f_is_d1 = boot && two_q;            // f_lp = d1_mvn.log_prob(X)  (SVO.py:230)
+  const bool sep_f = !boot;                      // a distinct f network exists
+
+  MlpS<DXP, DXP> q1s, fs;
+  MlpS<DXP, DYP> gs;
+  float* p = smem;
+  StepConsts<DXP>* C = reinterpret_cast<StepConsts<DXP>*>(p);
+  p += (sizeof(StepConsts<DXP>) / sizeof(float) + 3) & ~3;
+  if (!t0) p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
+  if (!t0 && sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
+  p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  float* scratch = p;
+
+  if (threadIdx.x < DXP) {
+    const int d = threadIdx.x;
+    const float s1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d];
+    const float s2 = a.sig[SIG_Q2 * 32 + d];
+    const float sfd = f_is_d1 ? s1 : a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+    const float i1 = 1.0f / s1, i2 = 1.0f / s2;
+    C->s1[d] = s1; C->sf[d] = sfd; C->inv1[d] = i1; C->inv2[d] = i2;
+    C->sp[d] = two_q ? 1.0f / (i1 + i2) : s1;
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + PSVO_MAX_DY) C->sg[threadIdx.x - 32] = a.sig[SIG_G * 32 + threadIdx.x - 32];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lp = 0.f, lf = 0.f, lg = 0.f;
+    for (int d = 0; d < Dx; ++d) { lp += logf(C->sp[d]); lf += logf(C->sf[d]); }
+    if (!poisson) for (int d = 0; d < Dy; ++d) lg += logf(C->sg[d]);
+    C->ld_p = lp; C->ld_f = lf; C->ld_g = lg;
+  }
+  __syncthreads();
+
+  const int tile = blockDim.x * PPT;
+  const int tiles_per_seq = (N + tile - 1) / tile;
+  const int work = a.B * tiles_per_seq;
+  const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
+  const float neg_logN = -logf((float)N);
+
+  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const int b = wi / tiles_per_seq;
+    const int n0 = (wi - b * tiles_per_seq) * tile;
+    const size_t bt = (size_t)b * a.T + a.t;
+
+    float x[PPT][DXP];        // parent, later the new particle
+    float mu1[PPT][DXP];
+    int n_of[PPT];
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
+      n_of[pp] = n0 + pp * blockDim.x + threadIdx.x;
+      const bool live = n_of[pp] < N;
+      if (!t0) {
+        const float* src = a.X_anc + ((bt - 1) * N + (live ? n_of[pp] : 0)) * Dx;
+        if (Dx == DXP) {
+#pragma unroll
+          for (int v = 0; v < DXP / 4; ++v) {
+            const float4 q = reinterpret_cast<const float4*>(src)[v];
+            x[pp][4 * v] = q.x; x[pp][4 * v + 1] = q.y; x[pp][4 * v + 2] = q.z; x[pp][4 * v + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DXP; ++d) x[pp][d] = d < Dx ? src[d] : 0.0f;
+        }
+      }
+    }
+
+    // ---- d1 mean: MLP q1 on the parent (t >= 1) or the per-sequence q0 mean (t = 0)
+    float muf[PPT][DXP];
+    if (!t0) {
+      mlp_eval<DXP, DXP, PPT>(q1s, x, mu1, scratch, a.scratch_half);
+      if (sep_f) mlp_eval<DXP, DXP, PPT>(fs, x, muf, scratch, a.scratch_half);
+    } else {
+#pragma unroll
+      for (int pp = 0; pp < PPT; ++pp)
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) {
+          mu1[pp][d] = d < Dx ? a.mu0[(size_t)b * Dx + d] : 0.0f;
+          if (!f_is_d1) muf[pp][d] = d < Dx ? a.muf0[(size_t)b * Dx + d] : 0.0f;
+        }
+    }
+    if (f_is_d1 || (!t0 && !sep_f)) {
+#pragma unroll
+      for (int pp = 0; pp < PPT; ++pp)
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) muf[pp][d] = mu1[pp][d];
+    }
+
+    // ---- proposal, sample, q / f log densities
+    float flp[PPT], qlp[PPT];
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
+      const bool live = n_of[pp] < N;
+      const size_t row = bt * N + (live ? n_of[pp] : 0);
+      float e[DXP];
+      if (a.eps != nullptr) {
+        const float* src = a.eps + row * Dx;
+        if (Dx == DXP) {
+#pragma unroll
+          for (int v = 0; v < DXP / 4; ++v) {
+            const float4 q = reinterpret_cast<const float4*>(src)[v];
+            e[4 * v] = q.x; e[4 * v + 1] = q.y; e[4 * v + 2] = q.z; e[4 * v + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DXP; ++d) e[d] = d < Dx ? src[d] : 0.0f;
+        }
+      } else {
+        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n_of[pp] : 0);
+#pragma unroll
+        for (int c = 0; c < DXP / 4; ++c) {
+          if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
+          else { e[4 * c] = e[4 * c + 1] = e[4 * c + 2] = e[4 * c + 3] = 0.f; }
+        }
+      }
+      float qs = 0.f, fsum = 0.f;
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) {
+        float m = mu1[pp][d];
+        if (two_q) {
+          const float m2 = d < Dx ? a.mu2_all[bt * Dx + d] : 0.0f;
+          m = C->sp[d] * (C->inv1[d] * mu1[pp][d] + C->inv2[d] * m2);
+        }
+        const float X = m + C->sp[d] * e[d];
+        const float zq = (X - m) / C->sp[d];
+        const float zf = (X - muf[pp][d]) / C->sf[d];
+        if (d < Dx) { qs = fmaf(zq, zq, qs); fsum = fmaf(zf, zf, fsum); }
+        x[pp][d] = d < Dx ? X : 0.0f;
+      }
+      qlp[pp] = -0.5f * qs - C->ld_p - cx;
+      flp[pp] = -0.5f * fsum - C->ld_f - cx;
+      if (live) {
+        float* dst = a.Xs + row * Dx;
+        if (Dx == DXP) {
+#pragma unroll
+          for (int v = 0; v < DXP / 4; ++v)
+            reinterpret_cast<float4*>(dst)[v] = make_float4(x[pp][4 * v], x[pp][4 * v + 1], x[pp][4 * v + 2], x[pp][4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < DXP; ++d) if (d < Dx) dst[d] = x[pp][d];
+        }
+      }
+    }
+
+    // ---- emission
+    float mug[PPT][DYP];
+    mlp_eval<DXP, DYP, PPT>(gs, x, mug, scratch, a.scratch_half);
+#pragma unroll
+    for (int pp = 0; pp < PPT; ++pp) {
+      const bool live = n_of[pp] < N;
+      float gsum = 0.f;
+#pragma unroll
+      for (int d = 0; d < DYP; ++d) {
+        if (d < Dy) {
+          const float y = a.obs[bt * Dy + d];
+          float z;
+          if (poisson) z = y - (softplus(mug[pp][d]) + 1e-6f);
+          else z = (y - mug[pp][d]) / C->sg[d];
+          gsum = fmaf(z, z, gsum);
+        }
+      }
+      const float g_lp = -0.5f * gsum - C->ld_g - cy;
+      // log_alpha = f + g - q ;  log_W = log_alpha + log Wbar_{t-1}   (SVO.py:97-98,151-152)
+      float lwb = neg_logN;
+      if (!t0 && a.logWbar != nullptr && live) lwb = a.logWbar[(size_t)b * N + n_of[pp]];
+      if (live) a.log_Ws[bt * N + n_of[pp]] = ((flp[pp] + g_lp) - qlp[pp]) + lwb;
+    }
+  }
+}
+
+template <int DXP, int DYP, int PPT>
+static int launch_propagate_t(const PropArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
+  auto kern = smc_propagate_kernel<DXP, DYP, PPT>;
+  static size_t configured = 0;          // per instantiation
+  if (smem > 48 * 1024 && smem > configured) {
+    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope ps_(PK_PROP, st);
+  kern<<<grid, block, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+PropPlan plan_propagate(const PropArgs& a) {
+  PropPlan pl;
+  const int DXP = pad_dx(a.Dx), DYP = pad_dy(a.Dy);
+  const bool sep_f = !(a.flags & PSVO_F_BOOTSTRAP);
+  const bool deep = a.q1.n_hidden >= 2 || a.g.n_hidden >= 2 || (sep_f && a.f.n_hidden >= 2);
+  const int64_t rows = (int64_t)a.B * a.N;
+  // two particles per thread once there is enough work to fill the machine twice over
+  pl.ppt = (!deep && rows >= (int64_t)2 * 256 * num_sms()) ? 2 : 1;
+  pl.block = deep ? 128 : 256;
+  while (pl.block > 32 && a.N <= pl.block / 2) pl.block /= 2;     // no idle warps on small particle counts
+  if (a.N < pl.block * pl.ppt) pl.ppt = 1;
+  size_t fl = 0;
+  auto add = [&](int din_pad, int dout_pad, const psvo_mlp& net) {
+    if (net.n_hidden == 0) return (size_t)(din_pad * dout_pad + dout_pad);
+    size_t n = (size_t)net.width[0] * din_pad + round4(net.width[0]);
+    for (int k = 1; k < net.n_hidden; ++k) n += round4(net.width[k - 1] * net.width[k]) + round4(net.width[k]);
+    return n + (size_t)net.width[net.n_hidden - 1] * dout_pad + dout_pad;
+  };
+  fl += 128;   // StepConsts upper bound (floats)
+  fl += add(DXP, DXP, a.q1);
+  if (sep_f) fl += add(DXP, DXP, a.f);
+  fl += add(DXP, DYP, a.g);
+  pl.scratch_half = 0;
+  if (deep) {
+    int hm = mlp_max_width(a.q1);
+    hm = hm > mlp_max_width(a.g) ? hm : mlp_max_width(a.g);
+    if (sep_f) hm = hm > mlp_max_width(a.f) ? hm : mlp_max_width(a.f);
+    pl.scratch_half = hm * pl.block * pl.ppt;
+    fl += 2 * (size_t)pl.scratch_half;
+  }
+  pl.smem = fl * sizeof(float);
+  const int tile = pl.block * pl.ppt;
+  const int64_t work = (int64_t)a.B * ((a.N + tile - 1) / tile);
+  const int per_sm = pl.smem > 100 * 1024 ? 1 : (pl.smem > 70 * 1024 ? 2 : 3);
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  pl.grid = (int)(work < cap ? work : cap);
+  if (pl.grid < 1) pl.grid = 1;
+  return pl;
+}
+
+int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
+  a.scratch_half = pl.scratch_half;
+  const int DXP = pad_dx(a.Dx), DYP = pad_dy(a.Dy);
+  PSVO_REQUIRE(pl.smem <= 227 * 1024, "MLP weights (%zu B) exceed one SM's shared memory", pl.smem);
+#define PSVO_CASE(X, Y)                                                                          \
+  if (DXP == X && DYP == Y) {                                                                    \
+    return pl.ppt == 2 ? launch_propagate_t<X, Y, 2>(a, pl.block, pl.grid, pl.smem, st)          \
+                       : launch_propagate_t<X, Y, 1>(a, pl.block, pl.grid, pl.smem, st);         \
+  }
+  PSVO_CASE(4, 4) PSVO_CASE(4, 8) PSVO_CASE(4, 16) PSVO_CASE(4, 32)
+  PSVO_CASE(8, 4) PSVO_CASE(8, 8) PSVO_CASE(8, 16) PSVO_CASE(8, 32)
+  PSVO_CASE(16, 4) PSVO_CASE(16, 8) PSVO_CASE(16, 16) PSVO_CASE(16, 32)
+#undef PSVO_CASE
+  return fail("unsupported padded dims Dx=%d Dy=%d", a.Dx, a.Dy);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: normalise + resample + gather.  One CTA per sequence.
+// shared memory: N floats (log weights) + N uint64 (inclusive fixed-point CDF) + scratch
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = a.N, Dx = a.Dx;
+  unsigned long long* sC = reinterpret_cast<unsigned long long*>(smraw);
+  float* sLW = reinterpret_cast<float*>(sC + N);
+  __shared__ unsigned long long sscr[33];
+  __shared__ float fscr[33];
+
+  const int b = blockIdx.x;
+  const size_t bt = (size_t)b * a.T + a.t;
+  const float* lw = a.log_Ws + bt * N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  float mx = -INFINITY;
+  for (int i = tid; i < N; i += nt) { const float v = lw[i]; sLW[i] = v; mx = fmaxf(mx, v); }
+  mx = block_max(mx, fscr);
+
+  // contiguous chunk per thread: local inclusive scan of the integer weights, then block offsets
+  const int ipt = (N + nt - 1) / nt;
+  const int lo = min(tid * ipt, N), hi = min(lo + ipt, N);
+  unsigned long long run = 0ull;
+  for (int i = lo; i < hi; ++i) { run += fixed_weight(sLW[i], mx); sC[i] = run; }
+  unsigned long long total;
+  const unsigned long long off = block_exscan_u64(run, sscr, &total);
+  for (int i = lo; i < hi; ++i) sC[i] += off;
+  __syncthreads();
+
+  // logsumexp from the same integer total: deterministic and independent of the thread count
+  const float lse = mx + (logf((float)total) - 32.0f * kLn2);
+  if (tid == 0) {
+    a.lse[bt] = lse;
+    a.logZ_b[b] = (a.t == 0 ? 0.0f : a.logZ_b[b]) + lse;
+  }
+
+  const bool resample = a.flags & PSVO_F_RESAMPLE;
+  const float* Xt = a.Xs + bt * N * Dx;
+  float* Xa = a.X_anc + bt * N * Dx;
+  for (int n = tid; n < N; n += nt) {
+    int anc = n;
+    if (resample) {
+      if (a.forced_anc != nullptr) {
+        anc = a.forced_anc[bt * N + n];
+        anc = anc < 0 ? 0 : (anc >= N ? N - 1 : anc);
+      } else {
+        uint32_t u24;
+        if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
+        else {
+          const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + n;
+          u24 = philox4x32_10(a.seed, gidx, 0u, 1u).v[0] >> 8;
+        }
+        anc = upper_bound_u64(sC, N, draw_threshold(total, u24));
+      }
+    } else {
+      a.logWbar[(size_t)b * N + n] = sLW[n] - lse;           // SVO.py:102,156 (IWAE keeps it differentiable)
+    }
+    a.anc[bt * N + n] = anc;
+    const float* src = Xt + (size_t)anc * Dx;
+    float* dst = Xa + (size_t)n * Dx;
+    if ((Dx & 3) == 0) {
+      for (int v = 0; v < Dx / 4; ++v) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
+    } else {
+      for (int d = 0; d < Dx; ++d) dst[d] = src[d];
+    }
+  }
+}
+
+int launch_resample(const ResampleArgs& a, cudaStream_t st) {
+  const int N = a.N;
+  int block = N >= 4096 ? 512 : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));
+  const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float));
+  PSVO_REQUIRE(smem <= 200 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 200 KiB)", N, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    PSVO_CUDA(cudaFuncSetAttribute(smc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope ps_(PK_RESAMPLE, st);
+  smc_resample_kernel<<<a.B, block, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace psvo

@@ -1,0 +1,59 @@
+// smc_kernels.h -- argument blocks and launchers shared by the CUDA translation units and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include "psvo_common.cuh"
+
+namespace psvo {
+
+// slots of the sigma block (32 floats each) computed by launch_sigma_block
+enum { SIG_Q0 = 0, SIG_Q1, SIG_Q2, SIG_F, SIG_G, SIG_BQI, SIG_Q1I, SIG_BQ2, SIG_SLOTS };
+
+struct SigmaSrc {
+  const float* con[SIG_SLOTS];
+  float smin[SIG_SLOTS];
+  int dim[SIG_SLOTS];
+};
+int launch_sigma_block(const SigmaSrc& src, float* sig, cudaStream_t st);
+
+struct PropArgs {
+  psvo_mlp q1, f, g;
+  const float* sig;        // sigma block
+  const float* obs;        // (B,T,Dy)
+  const float* mu2_all;    // (B,T,Dx) q2 means, or NULL when !two_q
+  const float* mu0;        // (B,Dx)   q0 mean
+  const float* muf0;       // (B,Dx)   f-dist mean of pre_x0 (only when !(bootstrap && two_q))
+  const float* eps;        // (B,T,N,Dx) or NULL -> Philox
+  const float* logWbar;    // (B,N) normalised log weights of t-1 (no-resample mode) or NULL -> -log N
+  const float* X_anc;      // (B,T,N,Dx) read at t-1
+  float* Xs;               // (B,T,N,Dx) written at t
+  float* log_Ws;           // (B,T,N)    written at t
+  unsigned long long seed;
+  int N, B, T, Dx, Dy, t, seq_offset, scratch_half;
+  unsigned flags;
+};
+struct PropPlan { int block, grid, ppt, scratch_half; size_t smem; };
+PropPlan plan_propagate(const PropArgs& a);
+int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st);
+
+struct ResampleArgs {
+  const float* log_Ws;     // (B,T,N)
+  const float* Xs;         // (B,T,N,Dx)
+  const float* u;          // (B,T,N) or NULL -> Philox
+  const int* forced_anc;   // (B,T,N) or NULL
+  float* X_anc;            // (B,T,N,Dx)
+  int* anc;                // (B,T,N)
+  float* lse;              // (B,T)
+  float* logZ_b;           // (B)
+  float* logWbar;          // (B,N) written when !resample
+  unsigned long long seed;
+  int N, B, T, Dx, t, seq_offset;
+  unsigned flags;
+};
+int launch_resample(const ResampleArgs& a, cudaStream_t st);
+
+// generic row MLP (mlp_rows.cu)
+int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, float* mu, cudaStream_t st);
+int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g_mu, int64_t rows,
+                             float* g_x, const psvo_mlp_grad* grads, cudaStream_t st);
+
+}  // namespace psvo

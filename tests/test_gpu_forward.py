@@ -1,0 +1,226 @@
+"""-m gpu parity tests of the forward particle filter and the stand-alone operators, through the C ABI
+(psvo_b200.functional -> ctypes -> libpsvo_b200.so) against the oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): ancestor indices bit-exact; log-weights / log_ZSMC 1e-5 relative (fp32)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import psvo_oracle as O
+from golden_io import case_names, load_case
+from gpu_util import to_dev, flags_of, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def Fn():
+    from psvo_b200 import functional
+    return functional
+
+
+def anc_from_golden(z):
+    Xs, Xa = z["Xs"], z["X_anc"]
+    return torch.from_numpy(np.abs(Xa[:, :, :, None, :] - Xs[:, :, None, :, :]).sum(-1).argmin(-1))
+
+
+# ------------------------------------------------------------------ stand-alone operators
+@pytest.mark.parametrize("K,n,rows", [(1, 5, 3), (7, 16, 4), (64, 64, 5), (1000, 333, 3), (4096, 4096, 2), (16384, 100, 1)])
+def test_resample_bit_exact(K, n, rows):
+    g = torch.Generator().manual_seed(K + n)
+    logits = (torch.randn(rows, K, generator=g) * 4 - 50).float()
+    logits[0, : max(1, K // 3)] -= 40.0                      # weights below the fixed-point resolution
+    u = torch.rand(rows, n, generator=g)
+    u[:, 0] = 0.0
+    u[:, -1] = float(np.nextafter(np.float32(1.0), np.float32(0.0)))
+    got = Fn().resample(logits.to(DEV), u.to(DEV)).cpu().numpy()
+    want = O.resample_idx(logits.numpy(), u.numpy())
+    assert (got == want).all(), "%d mismatching indices" % int((got != want).sum())
+
+
+def test_resample_rejects_cpu_tensors():
+    with pytest.raises(ValueError):
+        Fn().resample(torch.zeros(1, 4), torch.zeros(1, 4))
+
+
+def test_gather_matches_index_select():
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(3, 50, 5, generator=g)
+    idx = torch.randint(0, 50, (3, 70), generator=g)
+    got = Fn().gather(src.to(DEV), idx.to(DEV)).cpu()
+    want = torch.gather(src, 1, idx[:, :, None].expand(3, 70, 5))
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("hidden,din,dout,rows", [([], 4, 4, 37), ([32], 2, 2, 1000), ([64, 48], 128, 4, 50), ([256], 32, 16, 513)])
+def test_mlp_forward_and_backward(hidden, din, dout, rows):
+    g = torch.Generator().manual_seed(1)
+    net = O.make_net(g, din, hidden, dout)
+    x = torch.randn(rows, din, generator=g)
+    gm = torch.randn(rows, dout, generator=g)
+    Ws = [w.double().requires_grad_(True) for w in net.W]
+    bs = [b.double().requires_grad_(True) for b in net.b]
+    xd = x.double().requires_grad_(True)
+    mu = O.mlp_transform(O.Net(Ws, bs), xd)
+    mu.backward(gm.double())
+    f = Fn()
+    Wd = [w.to(DEV).requires_grad_(True) for w in net.W]
+    bd = [b.to(DEV).requires_grad_(True) for b in net.b]
+    xg = x.to(DEV).requires_grad_(True)
+    out = f.mlp_transform(Wd, bd, xg)
+    assert_close(out, mu.detach(), 1e-5, 1e-5, "mlp forward")
+    out.backward(gm.to(DEV))
+    assert_close(xg.grad, xd.grad, 1e-4, 1e-5, "g_x")
+    for k in range(len(Ws)):
+        scale = float(Ws[k].grad.abs().max())
+        assert_close(Wd[k].grad, Ws[k].grad, 1e-4, 1e-5 * max(scale, 1.0), "gW%d" % k)
+        assert_close(bd[k].grad, bs[k].grad, 1e-4, 1e-5 * max(float(bs[k].grad.abs().max()), 1.0), "gb%d" % k)
+
+
+def test_mvn_log_prob_logsumexp_sigma():
+    g = torch.Generator().manual_seed(2)
+    f = Fn()
+    x, mu = torch.randn(100, 16, generator=g), torch.randn(100, 16, generator=g)
+    s = torch.rand(16, generator=g) + 0.5
+    assert_close(f.mvn_log_prob(x.to(DEV), mu.to(DEV), s.to(DEV)), O.mvn_log_prob(x.double(), mu.double(), s.double()), 1e-5, 1e-5)
+    assert_close(f.mvn_log_prob(x.to(DEV), mu.to(DEV)), O.mvn_log_prob(x.double(), mu.double(), torch.ones(16, dtype=torch.float64)), 1e-5, 1e-5)
+    v = torch.randn(33, 4097, generator=g) * 10 - 100
+    assert_close(f.logsumexp(v.to(DEV)), torch.logsumexp(v.double(), -1), 1e-6, 1e-6)
+    sc = torch.tensor([5.0, -3.0, float("nan"), 0.3])
+    assert_close(f.get_sigma(sc.to(DEV), 1.0), O.get_sigma(sc.double(), 1.0), 1e-6, 1e-6)
+
+
+def test_philox_streams_moments_and_range():
+    f = Fn()
+    z = f.fill_normal(7, 0, 0, 200000, 16, DEV)
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.var()) - 1.0) < 1e-2
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.1
+    c = torch.corrcoef(z[:, :4].T)
+    assert float((c - torch.eye(4, device=DEV)).abs().max()) < 1e-2
+    u = f.fill_uniform(7, 1, 0, 1000000, DEV)
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0 and abs(float(u.mean()) - 0.5) < 2e-3
+    # counter-based: a shifted window reproduces the same draws
+    assert torch.equal(f.fill_uniform(7, 1, 1000, 50, DEV), u[1000:1050])
+
+
+# ------------------------------------------------------------------ forward filter vs golden vectors (reference's own code)
+@pytest.mark.parametrize("name", case_names())
+def test_forward_filter_golden_teacher_forced(name):
+    z, P, F, d = load_case(name, dtype=torch.float32)
+    N = int(z["N"])
+    forced = anc_from_golden(z) if F.resample_particles else None
+    r = Fn().smc_forward_raw(to_dev(P), flags_of(F), d["obs"].to(DEV), d["pre_obs"].to(DEV), d["pre_x0"].to(DEV), N,
+                             eps=d["eps"].to(DEV), u=None if d["u"] is None else d["u"].to(DEV), forced_anc=forced)
+    assert_close(r["Xs"], z["Xs"], 1e-5, 1e-5, "Xs")
+    assert_close(r["log_Ws"], z["log_Ws"], 1e-5, 1e-5, "log_Ws")
+    assert_close(r["X_anc"], z["X_anc"], 1e-5, 1e-5, "X_anc")
+    if str(z["cls"]) in ("SVO", "AESMC", "IWAE"):
+        assert abs(float(r["logZ_b"].mean()) - float(z["log_ZSMC"])) <= 1e-5 * abs(float(z["log_ZSMC"]))
+
+
+@pytest.mark.parametrize("name", [c for c in case_names() if c != "iwae_default"])
+def test_forward_filter_golden_free_running_ancestors(name):
+    """no teacher forcing: the kernel's own multinomial draws must reproduce the reference's ancestors"""
+    z, P, F, d = load_case(name, dtype=torch.float32)
+    N = int(z["N"])
+    r = Fn().smc_forward_raw(to_dev(P), flags_of(F), d["obs"].to(DEV), d["pre_obs"].to(DEV), d["pre_x0"].to(DEV), N,
+                             eps=d["eps"].to(DEV), u=d["u"].to(DEV))
+    want = anc_from_golden(z)
+    got = r["anc"].cpu().long()
+    assert torch.equal(got, want), "%d ancestor mismatches" % int((got != want).sum())
+    assert_close(r["log_Ws"], z["log_Ws"], 1e-5, 1e-5, "log_Ws")
+
+
+# ------------------------------------------------------------------ forward filter vs oracle on seeded inputs
+CONFIGS = [
+    # name, Dx, Dy, Dobs, Dx0, hidden, N, B, T, flags
+    ("c1_fhn", 2, 1, 64, 128, [32], 64, 1, 20, O.Flags()),
+    ("c2_lorenz", 3, 3, 3, 3, [32], 256, 2, 8, O.Flags()),
+    ("c3_lds_linear", 4, 4, 4, 4, [], 1024, 3, 6, O.Flags()),
+    ("c4_allen_poisson", 4, 1, 128, 256, [64], 2048, 1, 5, O.Flags(poisson_emission=True)),
+    ("c5_sweep", 16, 32, 32, 32, [256], 4096, 2, 3, O.Flags()),
+    ("ragged_n", 5, 7, 6, 9, [24], 777, 3, 4, O.Flags()),
+    ("single_particle", 2, 1, 1, 1, [8], 1, 2, 4, O.Flags()),
+    ("iwae_c2", 3, 3, 3, 3, [32], 300, 2, 6, O.Flags(resample_particles=False)),
+    ("no2q_noboot", 4, 2, 2, 4, [16], 200, 2, 5, O.Flags(use_bootstrap=False, use_2_q=False)),
+    ("deep_mlp", 3, 2, 4, 5, [16, 12, 8], 130, 2, 4, O.Flags()),
+]
+
+
+def make_case(Dx, Dy, Dobs, Dx0, hidden, N, B, T, F, seed=0):
+    P = O.make_params(seed, Dx, Dy, Dobs, Dx0, hidden, F)
+    g = torch.Generator().manual_seed(seed + 1)
+    obs = O.simulate_obs(P, F, B, T)
+    pre_obs = torch.randn(B, T, Dobs, generator=g)
+    pre_x0 = torch.randn(B, Dx0, generator=g)
+    eps = torch.randn(B, T, N, Dx, generator=g)
+    u = torch.rand(B, T, N, generator=g)
+    return P, obs, pre_obs, pre_x0, eps, u
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_forward_filter_vs_oracle(cfg):
+    name, Dx, Dy, Dobs, Dx0, hidden, N, B, T, F = cfg
+    P, obs, pre_obs, pre_x0, eps, u = make_case(Dx, Dy, Dobs, Dx0, hidden, N, B, T, F)
+    f = Fn()
+    r = f.smc_forward_raw(to_dev(P), flags_of(F), obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N,
+                          eps=eps.to(DEV), u=u.to(DEV))
+    anc = r["anc"].cpu().long()
+    assert int(anc.min()) >= 0 and int(anc.max()) < N
+    # (i) stage-wise bit-exact ancestry: the kernel's log-weight bits + the same u -> the oracle's rule
+    if F.resample_particles:
+        want = O.resample_idx(r["log_Ws"].cpu().numpy().reshape(B * T, N), u.numpy().reshape(B * T, N)).reshape(B, T, N)
+        assert (anc.numpy() == want).all(), "%d stage-wise ancestor mismatches" % int((anc.numpy() != want).sum())
+    # (ii) teacher-forced end to end against the fp64 oracle
+    P64 = O.params_to(P, torch.float64)
+    ref = O.smc_forward(P64, F, obs.double(), pre_obs.double(), pre_x0.double(), eps.double(), None,
+                        forced_anc=anc if F.resample_particles else None)
+    assert_close(r["Xs"], ref["Xs"], 1e-5, 2e-5, "Xs")
+    assert_close(r["log_Ws"], ref["log_Ws"], 1e-5, 1e-5 * float(ref["log_Ws"].abs().max()), "log_Ws")
+    assert_close(r["lse"], ref["lse"], 1e-5, 1e-5, "lse")
+    assert_close(r["logZ_b"], ref["logZ_b"], 1e-5, 1e-5, "logZ_b")
+    # (iii) gather consistency
+    want_anc = torch.gather(r["Xs"].cpu(), 2, anc[..., None].expand(B, T, N, Dx))
+    assert torch.equal(r["X_anc"].cpu(), want_anc)
+
+
+def test_philox_mode_equals_materialised_draws():
+    """production mode (in-kernel Philox) == parity mode fed with psvo_fill_normal / psvo_fill_uniform"""
+    name, Dx, Dy, Dobs, Dx0, hidden, N, B, T, F = CONFIGS[1]
+    P, obs, pre_obs, pre_x0, _, _ = make_case(Dx, Dy, Dobs, Dx0, hidden, N, B, T, F)
+    f = Fn()
+    Pd = to_dev(P)
+    a = f.smc_forward_raw(Pd, flags_of(F), obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N, seed=1234, seq_offset=5)
+    first = 5 * T * N
+    eps = f.fill_normal(1234, 0, first, B * T * N, Dx, DEV).view(B, T, N, Dx)
+    u = f.fill_uniform(1234, 1, first, B * T * N, DEV).view(B, T, N)
+    b = f.smc_forward_raw(Pd, flags_of(F), obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N, eps=eps, u=u)
+    for k in ("Xs", "X_anc", "anc", "log_Ws", "logZ_b"):
+        assert torch.equal(a[k], b[k]), k
+    # sharding invariance: sequence 1 alone with seq_offset 6 reproduces row 1
+    c = f.smc_forward_raw(Pd, flags_of(F), obs[1:].to(DEV), pre_obs[1:].to(DEV), pre_x0[1:].to(DEV), N, seed=1234, seq_offset=6)
+    assert torch.equal(c["log_Ws"][0], a["log_Ws"][1]) and torch.equal(c["anc"][0], a["anc"][1])
+
+
+def test_kalman_known_answer_on_gpu():
+    """config-3 analogue: linear-Gaussian SSM, AESMC bootstrap filter vs the analytic Kalman log-likelihood"""
+    from test_oracle import _lds
+    Dx, Dy, T, B, N = 4, 4, 25, 16, 4096
+    A, Cm, P = _lds(Dx, Dy, 0, torch.float32)
+    F = O.Flags(use_bootstrap=True, use_2_q=False)
+    g = torch.Generator().manual_seed(1)
+    x = 0.5 * torch.randn(B, Dx, generator=g, dtype=torch.float64)
+    ys = []
+    for t in range(T):
+        if t > 0:
+            x = x @ A + 0.5 * torch.randn(B, Dx, generator=g, dtype=torch.float64)
+        ys.append(x @ Cm + 0.3 * torch.randn(B, Dy, generator=g, dtype=torch.float64))
+    obs = torch.stack(ys, 1).float()
+    r = Fn().smc_forward_raw(to_dev(P), flags_of(F), obs.to(DEV), obs.to(DEV), torch.zeros(B, Dx, device=DEV), N, seed=99)
+    kls = [O.kalman_loglik(A.T.numpy(), np.zeros(Dx), 0.25 * np.eye(Dx), Cm.T.numpy(), np.zeros(Dy), 0.09 * np.eye(Dy),
+                           np.zeros(Dx), 0.25 * np.eye(Dx), obs[b].double().numpy()) for b in range(B)]
+    got = r["logZ_b"].cpu().double().numpy()
+    assert np.abs(got - np.array(kls)).max() < 0.5, (got, kls)
+    assert abs(got.mean() - np.mean(kls)) < 0.12
