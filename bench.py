@@ -144,6 +144,7 @@ def run_ours(args, w, rank, world, local_rank):
     smc = AESMC(model, FLAGS)
     obs_host = synth_obs(w, B, 1234, rank * B).pin_memory()
     obs_dev = obs_host.to(dev)
+    smc._build_nets(w["Dy"], w["Dy"], dev)        # AESMC feeds raw observations to q0 / q2
     P = model.dist_params()
     flags = Fn.flag_bits(True, True, True, bool(w.get("poisson", False)))
     bufs = {}

@@ -72,7 +72,7 @@ int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, f
   const size_t smem = 2 * (size_t)kRowTile * s.maxw * sizeof(float);
   PSVO_REQUIRE(smem <= 200 * 1024, "MLP layer width %d too large", s.maxw);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(mlp_rows_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
@@ -191,7 +191,7 @@ int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g
   const size_t smem = ((size_t)kRowTile * (s.sum_in + 2 * s.maxw) + s.n_param) * sizeof(float);
   PSVO_REQUIRE(smem <= 220 * 1024, "MLP too large for the row-backward kernel (%zu B shared memory)", smem);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(mlp_rows_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }

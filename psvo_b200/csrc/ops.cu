@@ -123,7 +123,7 @@ PSVO_API int psvo_resample(const float* logits, const float* u, int64_t rows, in
   const size_t smem = (size_t)K * (sizeof(unsigned long long) + sizeof(float));
   PSVO_REQUIRE(smem <= 200 * 1024, "psvo_resample: K=%d too large for the shared-memory CDF", K);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }

@@ -1,13 +1,512 @@
-// smc_backward.cu -- reverse mode of the forward filter (placeholder until the kernels land).
+// smc_backward.cu -- reverse mode of the forward particle filter.
+//
+// Reference: what optimizer.minimize(-log_ZSMC) (src/trainer.py:115-118) derives through SVO.SMC
+// (src/SMC/SVO.py:60-180): path-wise gradients through the reparameterised samples X_t = m + s*eps and through
+// the ancestor gather; tf.multinomial has no gradient, so nothing flows into the resampling logits
+// (SURVEY.md 3.5, App. A.8).  With resampling, log Wbar_{t-1} = -log N is a constant, so
+//     d logZ_b / d log_W_t[n] = softmax_n(log_W_t)[n].
+// Without resampling (IWAE) the per-step log-sum-exps telescope and d logZ_b / d log_alpha_t[n] is the FINAL
+// softmax weight of particle n for every t.
+//
+// Time runs backwards; per step two kernels (the MLP hidden activations are recomputed, never stored):
+//   bwd_emission : per particle, MLP g forward + reverse   -> gXg[b][n][:] = d/dX_t via the emission,
+//                  accumulates dW_g and the sigma_g statistic.
+//   bwd_proposal : per particle, MLP q1 (and f) forward + reverse, fusion / sample / f,q densities reverse
+//                  -> d/dX_anc_{t-1}, scattered (atomicAdd) onto the parents X_{t-1}[anc]; accumulates dW_q1,
+//                  dW_f, the per-(b,t) gradient of the q2 mean and the sigma statistics.
+// Afterwards the row-MLP reverse mode back-propagates the q2 / q0 / f(pre_x0) means to their parameters and
+// to pre_obs / pre_x0, and a tiny kernel maps the sigma statistics to d/d sigma_con.
+#include "mlp_bwd_tile.cuh"
 #include "smc_kernels.h"
+
+namespace psvo {
+
+// statistic slots accumulated by the step kernels (each 32 floats): index = slot*2 + tau  (tau = 0: t = 0)
+enum { ST_SP = 0, ST_I1, ST_I2, ST_SF, ST_SG, ST_SLOTS };
+
+struct BwdArgs {
+  psvo_mlp q1, f, g;
+  psvo_mlp_grad gq1, gf, gg;
+  const float* sig;
+  const float* obs; const float* mu2_all; const float* mu0; const float* muf0;
+  const float* Xs; const float* X_anc; const int* anc; const float* log_Ws; const float* lse;
+  const float* g_logZ_b;
+  float* gXg;        // (B,N,Dx) emission contribution to d/dX_t         (written by bwd_emission)
+  const float* gXin; // (B,N,Dx) children contribution to d/dX_t         (scattered by step t+1)
+  float* gXout;      // (B,N,Dx) d/dX_{t-1} accumulator (zeroed before the launch)
+  float* gmu2_all;   // (B,T,Dx)
+  float* gmu0;       // (B,Dx)
+  float* gmuf0;      // (B,Dx)
+  float* stats;      // [ST_SLOTS*2][32]
+  int N, B, T, Dx, Dy, t;
+  unsigned flags;
+};
+
+__device__ __forceinline__ float particle_weight_grad(const BwdArgs& a, int b, int n, bool live) {
+  // d L / d log_W_t[n]  (see file header)
+  if (!live) return 0.0f;
+  const bool resample = a.flags & PSVO_F_RESAMPLE;
+  const size_t bt = (size_t)b * a.T + (resample ? a.t : a.T - 1);
+  return expf(a.log_Ws[bt * a.N + n] - a.lse[bt]) * a.g_logZ_b[b];
+}
+
+template <int DXP, int DYP>
+__global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N;
+  const bool poisson = a.flags & PSVO_F_POISSON;
+  MlpS<DXP, DYP> gs;
+  MlpGradS<DXP, DYP> gg;
+  float* p = smem;
+  float* sg = p; p += 32;
+  float* sstat = p; p += 32;
+  p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  float* gacc0 = p;
+  p = mlp_grad_carve<DXP, DYP>(a.g, p, gg);
+  for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
+  float* stage = p;
+  if (threadIdx.x < 32) { sg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; sstat[threadIdx.x] = 0.0f; }
+  __syncthreads();
+
+  const int tile = blockDim.x;
+  const int tiles_per_seq = (N + tile - 1) / tile;
+  const int work = a.B * tiles_per_seq;
+  float st_sg[DYP];
+#pragma unroll
+  for (int d = 0; d < DYP; ++d) st_sg[d] = 0.0f;
+
+  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const int b = wi / tiles_per_seq;
+    const int n = (wi - b * tiles_per_seq) * tile + threadIdx.x;
+    const bool live = n < N;
+    const size_t bt = (size_t)b * a.T + a.t;
+    float x[DXP];
+#pragma unroll
+    for (int d = 0; d < DXP; ++d) x[d] = (live && d < Dx) ? a.Xs[(bt * N + n) * Dx + d] : 0.0f;
+    float xx[1][DXP], mug[1][DYP];
+#pragma unroll
+    for (int d = 0; d < DXP; ++d) xx[0][d] = x[d];
+    mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
+    const float gl = particle_weight_grad(a, b, n, live);
+    float G[DYP];
+#pragma unroll
+    for (int d = 0; d < DYP; ++d) {
+      G[d] = 0.0f;
+      if (d < Dy) {
+        const float y = a.obs[bt * Dy + d];
+        if (poisson) {
+          const float z = y - (softplus(mug[0][d]) + 1e-6f);
+          G[d] = gl * z * sigmoidf(mug[0][d]);
+        } else {
+          const float z = (y - mug[0][d]) / sg[d];
+          G[d] = gl * z / sg[d];
+          st_sg[d] += gl * (z * z - 1.0f) / sg[d];
+        }
+      }
+    }
+    float gx[DXP];
+    mlp_bwd_tile<DXP, DYP>(gs, gg, x, G, gx, stage);
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) if (d < Dx) a.gXg[((size_t)b * N + n) * Dx + d] = gx[d];
+    }
+  }
+  __syncthreads();
+  if (!poisson) {
+#pragma unroll
+    for (int d = 0; d < DYP; ++d) {
+      const float v = warp_sum(st_sg[d]);
+      if ((threadIdx.x & 31) == 0 && d < Dy) atomicAdd(&sstat[d], v);
+    }
+  }
+  __syncthreads();
+  if (!poisson && threadIdx.x < Dy) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, sstat[threadIdx.x]);
+  mlp_grad_flush<DXP, DYP>(a.g, gg, a.gg);
+}
+
+template <int DXP>
+__global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int Dx = a.Dx, N = a.N;
+  const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP;
+  const bool t0 = a.t == 0;
+  const bool f_is_d1 = boot && two_q, sep_f = !boot;
+  const int tau = t0 ? 0 : 1;
+
+  MlpS<DXP, DXP> q1s, fs;
+  MlpGradS<DXP, DXP> gq1, gf;
+  float* p = smem;
+  float* C = p; p += 5 * DXP;                 // s1 | sf | sp | inv1 | inv2
+  float* sred = p; p += 4 * 32;               // block partials: gm2 | gmu1 (t0) | gmuf (t0) | spare
+  float* sstat = p; p += 4 * 32;              // SP | I1 | I2 | SF
+  float* gacc0 = p;
+  if (!t0) {
+    p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
+    if (sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
+    gacc0 = p;
+    p = mlp_grad_carve<DXP, DXP>(a.q1, p, gq1);
+    if (sep_f) p = mlp_grad_carve<DXP, DXP>(a.f, p, gf);
+    for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
+  }
+  float* stage = p;
+  float *s1 = C, *sf = C + DXP, *sp = C + 2 * DXP, *inv1 = C + 3 * DXP, *inv2 = C + 4 * DXP;
+  if (threadIdx.x < DXP) {
+    const int d = threadIdx.x;
+    const float v1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d], v2 = a.sig[SIG_Q2 * 32 + d];
+    s1[d] = v1;
+    sf[d] = f_is_d1 ? v1 : a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+    inv1[d] = 1.0f / v1; inv2[d] = 1.0f / v2;
+    sp[d] = two_q ? 1.0f / (1.0f / v1 + 1.0f / v2) : v1;
+  }
+  for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) { sstat[i] = 0.0f; sred[i] = 0.0f; }
+  __syncthreads();
+
+  const int tile = blockDim.x;
+  const int tiles_per_seq = (N + tile - 1) / tile;
+  const int work = a.B * tiles_per_seq;
+  float st_sp[DXP], st_i1[DXP], st_i2[DXP], st_sf[DXP];
+#pragma unroll
+  for (int d = 0; d < DXP; ++d) st_sp[d] = st_i1[d] = st_i2[d] = st_sf[d] = 0.0f;
+
+  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const int b = wi / tiles_per_seq;
+    const int n = (wi - b * tiles_per_seq) * tile + threadIdx.x;
+    const bool live = n < N;
+    const size_t bt = (size_t)b * a.T + a.t;
+    const size_t bn = (size_t)b * N + (live ? n : 0);
+
+    float par[1][DXP], mu1[1][DXP], muf[1][DXP];
+    if (!t0) {
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) par[0][d] = (live && d < Dx) ? a.X_anc[((bt - 1) * N + n) * Dx + d] : 0.0f;
+      mlp_eval<DXP, DXP, 1>(q1s, par, mu1, nullptr, 0);
+      if (sep_f) mlp_eval<DXP, DXP, 1>(fs, par, muf, nullptr, 0);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) {
+        par[0][d] = 0.0f;
+        mu1[0][d] = d < Dx ? a.mu0[(size_t)b * Dx + d] : 0.0f;
+        if (!f_is_d1) muf[0][d] = d < Dx ? a.muf0[(size_t)b * Dx + d] : 0.0f;
+      }
+    }
+    if (f_is_d1 || (!t0 && !sep_f)) {
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) muf[0][d] = mu1[0][d];
+    }
+    const float gl = particle_weight_grad(a, b, n, live);
+
+    float gmu1[DXP], gmuf[DXP], gm2[DXP];
+#pragma unroll
+    for (int d = 0; d < DXP; ++d) {
+      gmu1[d] = gmuf[d] = gm2[d] = 0.0f;
+      if (d < Dx && live) {
+        const float X = a.Xs[(bt * N + n) * Dx + d];
+        const float m2 = two_q ? a.mu2_all[bt * Dx + d] : 0.0f;
+        const float A = inv1[d] * mu1[0][d] + inv2[d] * m2;              // m / sp  (two_q)
+        const float m = two_q ? sp[d] * A : mu1[0][d];
+        const float e = (X - m) / sp[d];
+        const float zf = (X - muf[0][d]) / sf[d];
+        const float gX = a.gXin[bn * Dx + d] + a.gXg[bn * Dx + d] - gl * zf / sf[d];
+        // X = m + sp*e ; -q_lp contributes +gl/sp to d/dsp, nothing to d/dm
+        st_sp[d] += gX * e + gl / sp[d] + (two_q ? gX * A : 0.0f);
+        st_sf[d] += gl * (zf * zf - 1.0f) / sf[d];
+        const float gmf = gl * zf / sf[d];                                // d f_lp / d muf
+        float g1 = two_q ? gX * sp[d] * inv1[d] : gX;                     // via m
+        if (two_q) {
+          st_i1[d] += gX * sp[d] * mu1[0][d];
+          st_i2[d] += gX * sp[d] * m2;
+          gm2[d] = gX * sp[d] * inv2[d];
+        }
+        if (f_is_d1 || (!t0 && !sep_f)) g1 += gmf;                        // muf IS mu1
+        else gmuf[d] = gmf;
+        gmu1[d] = g1;
+      }
+    }
+
+    // per-(b,t) gradient of the q2 mean; at t = 0 also of the per-sequence q0 / f means
+    if (two_q || t0) {
+      __syncthreads();
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) {
+        if (d < Dx) {
+          if (two_q) { const float v = warp_sum(gm2[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sred[d], v); }
+          if (t0) {
+            const float v1 = warp_sum(gmu1[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sred[32 + d], v1);
+            if (!f_is_d1) { const float v2 = warp_sum(gmuf[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sred[64 + d], v2); }
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < Dx) {
+        const int d = threadIdx.x;
+        if (two_q) { atomicAdd(a.gmu2_all + bt * Dx + d, sred[d]); sred[d] = 0.0f; }
+        if (t0) {
+          atomicAdd(a.gmu0 + (size_t)b * Dx + d, sred[32 + d]); sred[32 + d] = 0.0f;
+          if (!f_is_d1) { atomicAdd(a.gmuf0 + (size_t)b * Dx + d, sred[64 + d]); sred[64 + d] = 0.0f; }
+        }
+      }
+    }
+
+    if (!t0) {
+      float ga[DXP], ga2[DXP];
+      mlp_bwd_tile<DXP, DXP>(q1s, gq1, par[0], gmu1, ga, stage);
+      if (sep_f) {
+        mlp_bwd_tile<DXP, DXP>(fs, gf, par[0], gmuf, ga2, stage);
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) ga[d] += ga2[d];
+      }
+      if (live) {
+        const int parent = a.anc[(bt - 1) * N + n];
+        float* dst = a.gXout + ((size_t)b * N + parent) * Dx;
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) if (d < Dx) atomicAdd(dst + d, ga[d]);
+      }
+    }
+  }
+
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < DXP; ++d) {
+    if (d < Dx) {
+      float v = warp_sum(st_sp[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[d], v);
+      v = warp_sum(st_i1[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[32 + d], v);
+      v = warp_sum(st_i2[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[64 + d], v);
+      v = warp_sum(st_sf[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[96 + d], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < Dx) {
+    const int d = threadIdx.x;
+    atomicAdd(a.stats + (ST_SP * 2 + tau) * 32 + d, sstat[d]);
+    atomicAdd(a.stats + (ST_I1 * 2 + tau) * 32 + d, sstat[32 + d]);
+    atomicAdd(a.stats + (ST_I2 * 2 + tau) * 32 + d, sstat[64 + d]);
+    atomicAdd(a.stats + (ST_SF * 2 + tau) * 32 + d, sstat[96 + d]);
+  }
+  if (!t0) {
+    mlp_grad_flush<DXP, DXP>(a.q1, gq1, a.gq1);
+    if (sep_f) mlp_grad_flush<DXP, DXP>(a.f, gf, a.gf);
+  }
+}
+
+// statistics -> d/d sigma_con  (one block, 32 threads)
+struct SigmaGradArgs {
+  const float* stats; const float* sig;
+  const float* con[SIG_SLOTS]; float smin[SIG_SLOTS]; float* gcon[SIG_SLOTS];
+  int Dx, Dy; unsigned flags;
+};
+__global__ void sigma_grad_kernel(SigmaGradArgs a) {
+  const int d = threadIdx.x;
+  const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP, poisson = a.flags & PSVO_F_POISSON;
+  const bool f_is_d1 = boot && two_q;
+  float gs[SIG_SLOTS];
+  for (int k = 0; k < SIG_SLOTS; ++k) gs[k] = 0.0f;
+  if (d < a.Dx) {
+    for (int tau = 0; tau < 2; ++tau) {
+      const int d1 = tau == 0 ? SIG_Q0 : SIG_Q1;
+      const float s1 = a.sig[d1 * 32 + d], s2 = a.sig[SIG_Q2 * 32 + d];
+      const float acc_sp = a.stats[(ST_SP * 2 + tau) * 32 + d];
+      if (two_q) {
+        const float i1 = 1.0f / s1, i2 = 1.0f / s2, sp = 1.0f / (i1 + i2);
+        const float gi1 = a.stats[(ST_I1 * 2 + tau) * 32 + d] - sp * sp * acc_sp;
+        const float gi2 = a.stats[(ST_I2 * 2 + tau) * 32 + d] - sp * sp * acc_sp;
+        gs[d1] += -gi1 * i1 * i1;
+        gs[SIG_Q2] += -gi2 * i2 * i2;
+      } else {
+        gs[d1] += acc_sp;
+      }
+      const int owner = f_is_d1 ? d1 : (boot ? SIG_Q1 : SIG_F);
+      gs[owner] += a.stats[(ST_SF * 2 + tau) * 32 + d];
+    }
+  }
+  if (!poisson && d < a.Dy) gs[SIG_G] += a.stats[(ST_SG * 2 + 1) * 32 + d];
+  for (int k = 0; k < SIG_SLOTS; ++k) {
+    const int dim = k == SIG_G ? a.Dy : a.Dx;
+    if (a.gcon[k] == nullptr || a.con[k] == nullptr || d >= dim) continue;
+    const float sc = a.con[k][d];
+    const float sval = softplus(sc);
+    const bool pass = (sc == sc) && (sval > a.smin[k]);       // NaN scrub and clamp have zero gradient
+    if (pass) atomicAdd(a.gcon[k] + d, gs[k] * sigmoidf(sc));
+  }
+}
+
+template <int DXP, int DYP>
+static int launch_emission_t(const BwdArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
+  auto kern = bwd_emission_kernel<DXP, DYP>;
+  static size_t configured = 0;
+  if (smem > 40 * 1024 && smem > configured) {
+    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope ps_(PK_BWD, st);
+  kern<<<grid, block, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+template <int DXP>
+static int launch_proposal_t(const BwdArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
+  auto kern = bwd_proposal_kernel<DXP>;
+  static size_t configured = 0;
+  if (smem > 40 * 1024 && smem > configured) {
+    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ProfScope ps_(PK_BWD, st);
+  kern<<<grid, block, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+static size_t staged_floats(const psvo_mlp& net, int din_pad, int dout_pad) {
+  if (net.n_hidden == 0) return (size_t)din_pad * dout_pad + dout_pad;
+  return (size_t)net.width[0] * din_pad + round4(net.width[0]) + (size_t)net.width[0] * dout_pad + dout_pad;
+}
+
+struct BwdWs { float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp; size_t bytes; };
+static BwdWs carve_bwd(const psvo_dims* d, char* base) {
+  BwdWs w;
+  size_t off = 0;
+  auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
+  const size_t BT = (size_t)d->B * d->T, BN = (size_t)d->B * d->N;
+  w.sig = take(SIG_SLOTS * 32);
+  w.mu2_all = take(BT * d->Dx); w.mu0 = take((size_t)d->B * d->Dx); w.muf0 = take((size_t)d->B * d->Dx);
+  w.gmu2_all = take(BT * d->Dx); w.gmu0 = take((size_t)d->B * d->Dx); w.gmuf0 = take((size_t)d->B * d->Dx);
+  w.gXa = take(BN * d->Dx); w.gXb = take(BN * d->Dx); w.gXg = take(BN * d->Dx);
+  w.stats = take(ST_SLOTS * 2 * 32);
+  w.gx0tmp = take((size_t)d->B * d->Dx0);
+  w.bytes = off;
+  return w;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+int check_dims(const psvo_dims* d);
+int check_smc_params(const psvo_dims* d, const psvo_params* p);
+SigmaSrc sigma_src(const psvo_dims* d, const psvo_params* p, bool ffbsi);
+
+}  // namespace psvo
+
 using namespace psvo;
+
 extern "C" {
-PSVO_API size_t psvo_smc_backward_workspace_bytes(const psvo_dims* d, const psvo_params* p) { (void)d; (void)p; return 256; }
+
+PSVO_API size_t psvo_smc_backward_workspace_bytes(const psvo_dims* d, const psvo_params* p) {
+  (void)p;
+  if (d == nullptr) return 0;
+  return carve_bwd(d, nullptr).bytes;
+}
+
 PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const float* obs, const float* pre_obs,
                                const float* pre_x0, const float* eps, uint64_t seed, const float* Xs, const float* X_anc,
                                const int32_t* anc, const float* log_Ws, const float* lse, const float* g_logZ_b,
                                psvo_grads* grads, float* g_pre_obs, float* g_pre_x0, void* ws, size_t ws_bytes,
                                psvo_stream_t stream) {
-  return fail("psvo_smc_backward: not implemented in this build");
+  (void)eps; (void)seed;     // the noise is recovered as (X - m)/s from the stored particles
+  if (int e = check_dims(d)) return e;
+  if (int e = check_smc_params(d, p)) return e;
+  PSVO_REQUIRE(obs && pre_x0 && Xs && X_anc && anc && log_Ws && lse && g_logZ_b && grads && ws, "psvo_smc_backward: null buffer");
+  const bool two_q = d->flags & PSVO_F_TWO_Q, boot = d->flags & PSVO_F_BOOTSTRAP;
+  const bool f_is_d1 = boot && two_q, sep_f = !boot;
+  PSVO_REQUIRE(!two_q || pre_obs, "psvo_smc_backward: pre_obs is null but use_2_q is set");
+  const psvo_dist& fd = boot ? p->q1 : p->f;
+  PSVO_REQUIRE(p->q1.net.n_hidden <= 1 && p->g.net.n_hidden <= 1 && fd.net.n_hidden <= 1,
+               "psvo_smc_backward: per-particle networks (q1, f, g) with more than one hidden layer are not supported by the reverse-mode kernels yet");
+  const BwdWs w = carve_bwd(d, static_cast<char*>(ws));
+  PSVO_REQUIRE(ws_bytes >= w.bytes, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->B, T = d->T, N = d->N, Dx = d->Dx;
+  const size_t BT = (size_t)B * T, BN = (size_t)B * N;
+
+  // recompute the per-sequence means, clear the accumulators
+  if (int e = launch_sigma_block(sigma_src(d, p, false), w.sig, st)) return e;
+  if (two_q) if (int e = launch_mlp_rows_forward(p->q2.net, pre_obs, (int64_t)BT, w.mu2_all, st)) return e;
+  if (int e = launch_mlp_rows_forward(p->q0.net, pre_x0, B, w.mu0, st)) return e;
+  if (!f_is_d1) if (int e = launch_mlp_rows_forward(fd.net, pre_x0, B, w.muf0, st)) return e;
+  PSVO_CUDA(cudaMemsetAsync(w.gmu2_all, 0, BT * Dx * sizeof(float), st));
+  PSVO_CUDA(cudaMemsetAsync(w.gmu0, 0, (size_t)B * Dx * sizeof(float), st));
+  PSVO_CUDA(cudaMemsetAsync(w.gmuf0, 0, (size_t)B * Dx * sizeof(float), st));
+  PSVO_CUDA(cudaMemsetAsync(w.stats, 0, ST_SLOTS * 2 * 32 * sizeof(float), st));
+  PSVO_CUDA(cudaMemsetAsync(w.gXa, 0, BN * Dx * sizeof(float), st));
+
+  BwdArgs a;
+  a.q1 = p->q1.net; a.f = fd.net; a.g = p->g.net;
+  a.gq1 = grads->q1.net; a.gf = boot ? grads->q1.net : grads->f.net; a.gg = grads->g.net;
+  a.sig = w.sig; a.obs = obs; a.mu2_all = w.mu2_all; a.mu0 = w.mu0; a.muf0 = w.muf0;
+  a.Xs = Xs; a.X_anc = X_anc; a.anc = anc; a.log_Ws = log_Ws; a.lse = lse; a.g_logZ_b = g_logZ_b;
+  a.gXg = w.gXg; a.gmu2_all = w.gmu2_all; a.gmu0 = w.gmu0; a.gmuf0 = w.gmuf0; a.stats = w.stats;
+  a.N = N; a.B = B; a.T = T; a.Dx = Dx; a.Dy = d->Dy; a.flags = d->flags;
+
+  const int DXP = pad_dx(Dx), DYP = pad_dy(d->Dy);
+  // block size: as many particles per tile as shared memory allows (weights + gradient accumulator + staging)
+  auto pick_block = [&](size_t fixed_floats, int din, int dout, int* block, size_t* smem) -> int {
+    int P = 256;
+    while (P > 32 && N <= P / 2) P /= 2;
+    for (;; P /= 2) {
+      const size_t fl = fixed_floats + (size_t)2 * kBwdChunk * (P + 1) + (size_t)P * din + (size_t)P * dout;
+      if (fl * sizeof(float) <= 220 * 1024 || P == 32) { *block = P; *smem = fl * sizeof(float); break; }
+    }
+    PSVO_REQUIRE(*smem <= 227 * 1024, "psvo_smc_backward: networks too large for shared memory (%zu B)", *smem);
+    return 0;
+  };
+  int blkE, blkP; size_t smE, smP;
+  if (int e = pick_block(64 + 2 * staged_floats(a.g, DXP, DYP), DXP, DYP, &blkE, &smE)) return e;
+  const size_t fixedP = 5 * DXP + 256 + 2 * staged_floats(a.q1, DXP, DXP) + (sep_f ? 2 * staged_floats(a.f, DXP, DXP) : 0);
+  if (int e = pick_block(fixedP, DXP, DXP, &blkP, &smP)) return e;
+  auto grid_of = [&](int block) {
+    const int64_t work = (int64_t)B * ((N + block - 1) / block);
+    const int64_t cap = num_sms();
+    return (int)(work < cap ? work : cap);
+  };
+
+  float* gXin = w.gXa;      // children contribution for the current step (zero at t = T-1)
+  float* gXout = w.gXb;
+  for (int t = T - 1; t >= 0; --t) {
+    a.t = t; a.gXin = gXin; a.gXout = gXout;
+    if (t > 0) PSVO_CUDA(cudaMemsetAsync(gXout, 0, BN * Dx * sizeof(float), st));
+    int rc = -1;
+#define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, grid_of(blkE), smE, st);
+    PSVO_CASE_E(4, 4) PSVO_CASE_E(4, 8) PSVO_CASE_E(4, 16) PSVO_CASE_E(4, 32)
+    PSVO_CASE_E(8, 4) PSVO_CASE_E(8, 8) PSVO_CASE_E(8, 16) PSVO_CASE_E(8, 32)
+    PSVO_CASE_E(16, 4) PSVO_CASE_E(16, 8) PSVO_CASE_E(16, 16) PSVO_CASE_E(16, 32)
+#undef PSVO_CASE_E
+    if (rc) return rc;
+    rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP), smP, st)
+                  : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP), smP, st)
+                              : launch_proposal_t<16>(a, blkP, grid_of(blkP), smP, st));
+    if (rc) return rc;
+    float* tmp = gXin; gXin = gXout; gXout = tmp;
+  }
+
+  // per-sequence networks: q2 over (b,t) rows, q0 (and f on pre_x0) over b rows
+  if (two_q) {
+    if (int e = launch_mlp_rows_backward(p->q2.net, pre_obs, w.gmu2_all, (int64_t)BT, g_pre_obs, &grads->q2.net, st)) return e;
+  } else if (g_pre_obs != nullptr && pre_obs != nullptr) {
+    PSVO_CUDA(cudaMemsetAsync(g_pre_obs, 0, BT * d->Dobs * sizeof(float), st));
+  }
+  if (int e = launch_mlp_rows_backward(p->q0.net, pre_x0, w.gmu0, B, g_pre_x0, &grads->q0.net, st)) return e;
+  if (!f_is_d1) {
+    const psvo_mlp_grad* gfd = boot ? &grads->q1.net : &grads->f.net;
+    if (int e = launch_mlp_rows_backward(fd.net, pre_x0, w.gmuf0, B, g_pre_x0 ? w.gx0tmp : nullptr, gfd, st)) return e;
+    if (g_pre_x0 != nullptr) {
+      ProfScope ps_(PK_BWD, st);
+      add_inplace_kernel<<<ceil_div((int64_t)B * d->Dx0, 256), 256, 0, st>>>(g_pre_x0, w.gx0tmp, (long long)B * d->Dx0);
+      PSVO_LAUNCH_CHECK();
+    }
+  }
+
+  SigmaGradArgs sa;
+  sa.stats = w.stats; sa.sig = w.sig; sa.Dx = Dx; sa.Dy = d->Dy; sa.flags = d->flags;
+  const SigmaSrc src = sigma_src(d, p, false);
+  for (int k = 0; k < SIG_SLOTS; ++k) { sa.con[k] = src.con[k]; sa.smin[k] = src.smin[k]; sa.gcon[k] = nullptr; }
+  sa.gcon[SIG_Q0] = grads->q0.sigma_con; sa.gcon[SIG_Q1] = grads->q1.sigma_con; sa.gcon[SIG_Q2] = grads->q2.sigma_con;
+  sa.gcon[SIG_F] = grads->f.sigma_con; sa.gcon[SIG_G] = grads->g.sigma_con;
+  {
+    ProfScope ps_(PK_BWD, st);
+    sigma_grad_kernel<<<1, 32, 0, st>>>(sa);
+    PSVO_LAUNCH_CHECK();
+  }
+  return 0;
 }
-}
+
+}  // extern "C"

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
     C->s1[d] = s1; C->sf[d] = sfd; C->inv1[d] = i1; C->inv2[d] = i2;
     C->sp[d] = two_q ? 1.0f / (i1 + i2) : s1;
   }
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + PSVO_MAX_DY) C->sg[threadIdx.x - 32] = a.sig[SIG_G * 32 + threadIdx.x - 32];
+  for (int i = threadIdx.x; i < PSVO_MAX_DY; i += blockDim.x) C->sg[i] = a.sig[SIG_G * 32 + i];
   __syncthreads();
   if (threadIdx.x == 0) {
     float lp = 0.f, lf = 0.f, lg = 0.f;
@@ -226,7 +226,7 @@ template <int DXP, int DYP, int PPT>
 static int launch_propagate_t(const PropArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
   auto kern = smc_propagate_kernel<DXP, DYP, PPT>;
   static size_t configured = 0;          // per instantiation
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
@@ -368,7 +368,7 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float));
   PSVO_REQUIRE(smem <= 200 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 200 KiB)", N, smem);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(smc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
