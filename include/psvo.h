@@ -146,7 +146,9 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p,
  *   eps_bw (B,T,M,N,Dx), u_pick (B,T,N), u_res (B,T,N; PSVOwR only) or NULL -> Philox(seed).
  *   forced_pick / forced_anc2 (B,T,N) or NULL: teacher forcing.
  * Outputs: bw_Xs (B,T,N,Dx), pick (B,T,N); PSVO: f_lp, g_lp, Omega (B,T,N); PSVOwR: bw_log_W in out_a,
- *   bw_X_anc (B,T,N,Dx) and anc2; logZ_b (B). Unused outputs may be NULL. */
+ *   bw_X_anc (B,T,N,Dx) and anc2; omega_all (B,T,N,M) or NULL = the normalised log omega of every candidate
+ *   (the logits of the 1-of-M pick; tests use it for the stage-wise bit-exactness check); logZ_b (B).
+ *   Outputs of the other variant may be NULL. */
 PSVO_API size_t psvo_ffbsi_workspace_bytes(const psvo_dims* d, const psvo_params* p);
 PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p,
                        const float* obs, const float* bs_feat, const float* pre_x0,
@@ -154,7 +156,7 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p,
                        const float* eps_bw, const float* u_pick, const float* u_res,
                        const int32_t* forced_pick, const int32_t* forced_anc2, uint64_t seed,
                        float* bw_Xs, int32_t* pick, float* f_lp, float* g_lp, float* Omega_or_bw_log_W,
-                       float* bw_X_anc, int32_t* anc2, float* logZ_b,
+                       float* bw_X_anc, int32_t* anc2, float* omega_all, float* logZ_b,
                        void* ws, size_t ws_bytes, psvo_stream_t stream);
 
 /* ---- stand-alone operators (API parity + unit tests) ----------------------------------------------------

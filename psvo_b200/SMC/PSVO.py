@@ -1,0 +1,88 @@
+"""PSVO: particle-smoothing objective -- forward filter + FFBSi-style backward simulation with an M-sample proposal.
+
+Interface of src/SMC/PSVO.py: PSVO(model, FLAGS), get_log_ZSMC(obs, hidden) -> (log_ZSMC, {"Xs": bw_Xs (B,T,N,Dx)}),
+backward_simulation_w_proposal(Xs, log_Ws, obs), compute_log_ZSMC(f, g, Omega), BS_preprocess_obs(obs).
+Round-1 status: the forward value runs on the GPU kernels (psvo_ffbsi_forward); its reverse mode
+(psvo_ffbsi_backward) is not built yet, so the returned log_ZSMC raises if back-propagated."""
+import torch
+
+from .. import functional as Fn
+from .SVO import SVO
+
+
+class _NoGradYet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, *leaves):
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("reverse mode of the FFBSi backward simulation (psvo_ffbsi_backward) is not built yet; "
+                                  "SVO / AESMC / IWAE objectives are differentiable")
+
+
+class PSVO(SVO):
+    with_resampling = False
+
+    def __init__(self, model, FLAGS, name="log_ZSMC"):
+        SVO.__init__(self, model, FLAGS, name="log_ZSMC")
+        self.n_particles_for_BSim_proposal = FLAGS.n_particles_for_BSim_proposal
+        self.smooth_obs = False
+        self.BSim_use_single_RNN = FLAGS.BSim_use_single_RNN
+        if self.BSim_use_single_RNN:
+            raise NotImplementedError("BSim_use_single_RNN=True is broken in the reference (self.y_smoother_f is unset "
+                                      "when smooth_obs=False, src/SMC/PSVO.py:208-212)")
+        self.q1_inv = model.q1_inv_dist
+        self.BSim_q_init = model.Bsim_q_init_dist
+        self.BSim_q2 = model.BSim_q2_dist
+
+    def get_log_ZSMC(self, obs, hidden=None, eps=None, uniforms=None, forced_ancestors=None, seed=None,
+                     eps_bw=None, uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None):
+        with torch.no_grad():
+            _, aux = self._filter(obs, eps, uniforms, forced_ancestors, seed, out)        # PSVO.py:39
+            used_seed = self._last_seed
+            bs = self.backward_simulation_w_proposal(aux["Xs"], aux["log_Ws"], obs, lse=aux["lse"], eps_bw=eps_bw,
+                                                     uniforms_pick=uniforms_pick, uniforms_res=uniforms_res,
+                                                     forced_pick=forced_pick, forced_anc2=forced_anc2, seed=used_seed)
+        self.last = dict(filter=aux, bsim=bs)
+        log_ZSMC = _NoGradYet.apply(bs["logZ_b"].mean(), *[p for p in self.model.parameters()][:1])
+        Xs = bs["bw_X_anc"] if self.with_resampling else bs["bw_Xs"]                      # PSVO.py:43, PSVOwR.py:43
+        return log_ZSMC, {"Xs": Xs}
+
+    def _filter(self, obs, eps, u, forced, seed, out):
+        if seed is None:
+            seed = (self.seed << 20) + self._calls
+            self._calls += 1
+        self._last_seed = seed
+        return SVO._filter(self, obs, eps, u, forced, seed, out)
+
+    def BS_preprocess_obs(self, obs):
+        """PSVO.py:205-216: bi-LSTM features for the backward proposal (the X0 feature is discarded)."""
+        return self.preprocess_obs_w_bRNN(obs)
+
+    def backward_simulation_w_proposal(self, Xs, log_Ws, obs, lse=None, eps_bw=None, uniforms_pick=None,
+                                       uniforms_res=None, forced_pick=None, forced_anc2=None, seed=0):
+        """Xs (B,T,N,Dx) pre-resampling particles, log_Ws (B,T,N) from the forward filter.  Returns the dict of
+        psvo_ffbsi_forward outputs: bw_Xs, pick, logZ_b and f_lp/g_lp/Omega (PSVO) or bw_log_W/bw_X_anc/anc2 (PSVOwR)."""
+        m = self.model
+        if lse is None:
+            lse = Fn.logsumexp(log_Ws)
+        _, feats = self.BS_preprocess_obs(obs)
+        feats = feats.contiguous()
+        m.BSim_q_init_tran.build(feats.shape[-1], obs.device)
+        m.BSim_q2_tran.build(feats.shape[-1], obs.device)
+        m.to(obs.device)
+        flags = Fn.flag_bits(m.use_bootstrap, m.use_2_q, True, m.poisson_emission, self.with_resampling)
+        return Fn.ffbsi_forward_raw(m.dist_params(), flags, obs, feats.detach(), self.preprocessed_X0.detach(), Xs, log_Ws,
+                                    lse, self.n_particles_for_BSim_proposal, eps_bw=eps_bw, u_pick=uniforms_pick,
+                                    u_res=uniforms_res, forced_pick=forced_pick, forced_anc2=forced_anc2, seed=seed,
+                                    seq_offset=self.seq_offset)
+
+    @staticmethod
+    def compute_log_ZSMC(f_log_probs, g_log_probs, bw_log_Omegas):
+        """PSVO.py:52-67 on (time, n_particles, batch_size) tensors."""
+        T, N, B = f_log_probs.shape
+        joint = (f_log_probs + g_log_probs).sum(0)
+        prop = bw_log_Omegas.sum(0)
+        lse = Fn.logsumexp((joint - prop).t().contiguous())
+        return (lse - torch.log(torch.tensor(float(N), device=lse.device))).mean()

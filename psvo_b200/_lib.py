@@ -56,7 +56,7 @@ SIGNATURES = {
                                     C.POINTER(psvo_grads), _vp, _vp, _vp, _sz, _vp]),
     "psvo_ffbsi_workspace_bytes": (_sz, [_dp, _pp]),
     "psvo_ffbsi_forward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
-                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psvo_resample": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "psvo_gather": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "psvo_mlp_forward": (C.c_int, [C.POINTER(psvo_mlp), _vp, _i64, _vp, _vp]),

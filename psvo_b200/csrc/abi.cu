@@ -205,7 +205,7 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
   ResampleArgs ra;
   ra.log_Ws = log_Ws; ra.Xs = Xs; ra.u = u; ra.forced_anc = forced_anc; ra.X_anc = X_anc; ra.anc = anc;
   ra.lse = lse; ra.logZ_b = logZ_b; ra.logWbar = w.logWbar; ra.seed = seed;
-  ra.N = d->N; ra.B = d->B; ra.T = d->T; ra.Dx = d->Dx; ra.t = 0; ra.seq_offset = d->seq_offset; ra.flags = d->flags;
+  ra.N = d->N; ra.B = d->B; ra.T = d->T; ra.Dx = d->Dx; ra.t = 0; ra.seq_offset = d->seq_offset; ra.flags = d->flags; ra.stream_id = 1u;
 
   for (int t = 0; t < d->T; ++t) {
     pa.t = t; ra.t = t;

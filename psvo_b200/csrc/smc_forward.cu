@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
   // logsumexp from the same integer total: deterministic and independent of the thread count
   const float lse = mx + (logf((float)total) - 32.0f * kLn2);
   if (tid == 0) {
-    a.lse[bt] = lse;
-    a.logZ_b[b] = (a.t == 0 ? 0.0f : a.logZ_b[b]) + lse;
+    if (a.lse != nullptr) a.lse[bt] = lse;
+    if (a.logZ_b != nullptr) a.logZ_b[b] = (a.t == 0 ? 0.0f : a.logZ_b[b]) + lse;
   }
 
   const bool resample = a.flags & PSVO_F_RESAMPLE;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
         if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
         else {
           const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + n;
-          u24 = philox4x32_10(a.seed, gidx, 0u, 1u).v[0] >> 8;
+          u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
         }
         anc = upper_bound_u64(sC, N, draw_threshold(total, u24));
       }

@@ -48,6 +48,7 @@ struct ResampleArgs {
   unsigned long long seed;
   int N, B, T, Dx, t, seq_offset;
   unsigned flags;
+  unsigned stream_id;      // Philox stream of the uniforms (1 forward filter, 4 PSVOwR second resampling)
 };
 int launch_resample(const ResampleArgs& a, cudaStream_t st);
 

@@ -196,6 +196,52 @@ def smc_backward_raw(P: dict, flags: int, obs, pre_obs, pre_x0, N, eps, seed, se
 
 
 # ----------------------------------------------------------------------------------------------------
+# FFBSi backward simulation
+# ----------------------------------------------------------------------------------------------------
+def ffbsi_forward_raw(P: dict, flags: int, obs, bs_feat, pre_x0, Xs, log_Ws, lse, M, eps_bw=None, u_pick=None,
+                      u_res=None, forced_pick=None, forced_anc2=None, seed=0, seq_offset=0, want_omega_all=False):
+    """psvo_ffbsi_forward (PSVO, or PSVOwR when flags has F_WITH_RESAMPLING).  Returns a dict of device tensors."""
+    lib = L.load()
+    obs, bs_feat, pre_x0 = _f32(obs, "obs"), _f32(bs_feat, "bs_feat"), _f32(pre_x0, "pre_x0")
+    Xs, log_Ws, lse = _f32(Xs, "Xs"), _f32(log_Ws, "log_Ws"), _f32(lse, "lse")
+    B, T, N, Dx = Xs.shape
+    Dy = obs.shape[-1]
+    dev = obs.device
+    keep = []
+    ps = params_struct(P, keep)
+    dims = make_dims(N, B, T, Dx, Dy, 0, pre_x0.shape[-1], flags, M=M, Dfeat=bs_feat.shape[-1], seq_offset=seq_offset)
+    wr = bool(flags & L.F_WITH_RESAMPLING)
+    eps_bw, u_pick, u_res = _f32(eps_bw, "eps_bw"), _f32(u_pick, "u_pick"), _f32(u_res, "u_res")
+    if eps_bw is not None and tuple(eps_bw.shape) != (B, T, M, N, Dx):
+        raise ValueError("eps_bw must be (B,T,M,N,Dx)")
+    i32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.int32).contiguous()
+    forced_pick, forced_anc2 = i32(forced_pick), i32(forced_anc2)
+    f32 = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    out = dict(bw_Xs=f32(B, T, N, Dx), pick=torch.empty(B, T, N, device=dev, dtype=torch.int32), logZ_b=f32(B))
+    if wr:
+        out.update(bw_log_W=f32(B, T, N), bw_X_anc=f32(B, T, N, Dx), anc2=torch.empty(B, T, N, device=dev, dtype=torch.int32))
+        f_lp = g_lp = None
+        oa, xa, a2 = out["bw_log_W"], out["bw_X_anc"], out["anc2"]
+    else:
+        out.update(f_lp=f32(B, T, N), g_lp=f32(B, T, N), Omega=f32(B, T, N))
+        f_lp, g_lp, oa, xa, a2 = out["f_lp"], out["g_lp"], out["Omega"], None, None
+    omega_all = f32(B, T, N, M) if want_omega_all else None
+    if omega_all is not None:
+        out["omega_all"] = omega_all
+    wsb = lib.psvo_ffbsi_workspace_bytes(C.byref(dims), C.byref(ps))
+    ws = torch.empty(max(wsb, 256), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        rc = lib.psvo_ffbsi_forward(C.byref(dims), C.byref(ps), _ptr(obs), _ptr(bs_feat), _ptr(pre_x0), _ptr(Xs),
+                                    _ptr(log_Ws), _ptr(lse), _ptr(eps_bw), _ptr(u_pick), _ptr(u_res),
+                                    _ptr(forced_pick), _ptr(forced_anc2), C.c_uint64(seed & (2 ** 64 - 1)),
+                                    _ptr(out["bw_Xs"]), _ptr(out["pick"]), _ptr(f_lp), _ptr(g_lp), _ptr(oa), _ptr(xa),
+                                    _ptr(a2), _ptr(omega_all), _ptr(out["logZ_b"]), _ptr(ws), C.c_size_t(ws.numel()),
+                                    _stream())
+    L.check(rc, "psvo_ffbsi_forward")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
 # stand-alone operators
 # ----------------------------------------------------------------------------------------------------
 def resample(logits, u):
