@@ -316,6 +316,9 @@ def backward_simulation(P: Params, F: Flags, obs, bs_feat, pre_x0, Xs, log_Ws, e
         lp = -0.5 * (z * z).sum(-1) - torch.log(s_f).sum() - 0.5 * Dx * LOG_2PI
         return logsumexp(lp + wbar[:, None, None, :], dim=3)
 
+    if u_bw is None:
+        assert forced_pick is not None, "either u_bw or forced_pick is required"
+        u_bw = torch.zeros(B, T, N)
     bw_Xs = [None] * T
     f_lps, g_lps, Omegas = [None] * T, [None] * T, [None] * T
     bw_log_Ws, bw_X_ancs = [None] * T, [None] * T

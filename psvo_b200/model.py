@@ -86,4 +86,5 @@ class SSM(torch.nn.Module):
             P["bsim_q_init"] = self.Bsim_q_init_dist.dist_params()
             P["q1_inv"] = self.q1_inv_dist.dist_params()
             P["bsim_q2"] = self.BSim_q2_dist.dist_params()
-        return P
+        # lazily built networks (Keras infers the input width at first call) only exist once they have been fed
+        return {k: v for k, v in P.items() if len(v.Ws) > 0}
