@@ -202,6 +202,9 @@ PSVO_API int psvo_fill_uniform(uint64_t seed, int32_t stream_id, int64_t first_p
 
 PSVO_API int psvo_mlp_forward(const psvo_mlp* net, const float* x, int64_t rows, float* mu, psvo_stream_t stream) {
   PSVO_REQUIRE(net && x && mu, "psvo_mlp_forward: null pointer");
+  // particle-shaped nets with many rows run on the tensor cores (tc_mlp.cu), everything else on the row kernel
+  if (rows >= 256 && rows < (1LL << 31) && tc_mlp_supported(*net))
+    return launch_particle_mlp_tc(*net, x, 0, 1, (int)rows, mu, (cudaStream_t)stream);
   return launch_mlp_rows_forward(*net, x, rows, mu, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,129 @@
+// tc_common.cuh -- sm_100a tensor-core plumbing: tcgen05.mma / TMEM / mbarrier wrappers (inline PTX) and the
+// shared-memory operand layout used by the tensor-core MLP paths.
+//
+// Precision scheme ("bf16x3"): an fp32 operand x is split as x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+// (16 mantissa bits in total).  A product a*w is evaluated as  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  by three
+// kind::f16 MMAs accumulating in fp32 TMEM; the dropped a_lo*w_lo term is 2^-16 relative.  This keeps the MLP
+// outputs within ~1e-6 relative of an fp32 evaluation (the path's parity bar is 1e-5) at one third of the bf16
+// tensor rate -- about 7x the FP32 CUDA-core peak.
+//
+// Operand layout (both A = activations [rows x K] and B = weights [N x K], K-major, no swizzle):
+//   element (r, k) lives at  base + (k/8) * (ROWS*16 B) + r * 16 B + (k%8) * 2 B
+// i.e. K-groups of 8 elements are the slow index; inside a K-group every row owns one 16-byte chunk.  In UMMA
+// terms the 8x16B core matrices of consecutive row groups are contiguous (SBO = 128 B) and consecutive K-groups
+// are ROWS*16 B apart (LBO).  A thread that owns row r writes 8 consecutive k of its row with ONE conflict-free
+// 16-byte store.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace psvo {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- shared-memory matrix descriptor (K-major, SWIZZLE_NONE) --------------------------------------------
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// ---- instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major -----------------------
+// [4,6) c_format=1(f32) | [7,10) a_format=1(bf16) | [10,13) b_format=1(bf16) | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+// all MMAs issued so far by this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+               :: "r"(smem_u32(mbar)) : "memory");
+}
+
+// ---- TMEM -------------------------------------------------------------------------------------------------
+// one full warp allocates `cols` (power of two >= 32) columns; the base address lands in *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// make this thread's st.shared visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// this warp's 32 lanes x 16 consecutive columns, one row (lane) per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}\n"
+      :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+
+// ---- bf16 hi/lo split ---------------------------------------------------------------------------------------
+// 8 consecutive k of one row -> two 16-byte chunks (hi, lo)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// stage an fp32 Keras kernel W[in][out] (row-major, `out` contiguous) as the B operand [N = out rows][K = in],
+// hi and lo, zero padded to (NP rows, KP k).  Cooperative over the block.
+__device__ __forceinline__ void stage_weight_bf16x2(const float* __restrict__ W, int n_in, int n_out, int KP, int NP,
+                                                    unsigned char* hi, unsigned char* lo) {
+  for (int i = threadIdx.x; i < NP * KP; i += blockDim.x) {
+    const int n = i % NP, k = i / NP;                       // consecutive threads -> consecutive out (coalesced read)
+    const float w = (n < n_out && k < n_in) ? __ldg(W + (size_t)k * n_out + n) : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const size_t off = (size_t)(k >> 3) * (NP * 16) + (size_t)n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+  }
+}
+
+}  // namespace tc
+}  // namespace psvo

@@ -54,7 +54,10 @@ def test_gather_matches_index_select():
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("hidden,din,dout,rows", [([], 4, 4, 37), ([32], 2, 2, 1000), ([64, 48], 128, 4, 50), ([256], 32, 16, 513)])
+@pytest.mark.parametrize("hidden,din,dout,rows", [([], 4, 4, 37), ([32], 2, 2, 100), ([64, 48], 128, 4, 50), ([256], 32, 16, 513),
+                                                   # shapes that take the tcgen05 tensor-core path (d_in<=16, H%16==0, rows>=256)
+                                                   ([256], 16, 16, 1000), ([256], 16, 32, 4099), ([64], 4, 1, 300), ([32], 2, 2, 1000),
+                                                   ([128], 3, 3, 256)])
 def test_mlp_forward_and_backward(hidden, din, dout, rows):
     g = torch.Generator().manual_seed(1)
     net = O.make_net(g, din, hidden, dout)
