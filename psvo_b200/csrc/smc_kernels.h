@@ -57,6 +57,10 @@ int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, f
 int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g_mu, int64_t rows,
                              float* g_x, const psvo_mlp_grad* grads, cudaStream_t st);
 
+// tensor-core (tcgen05) propagate step (smc_propagate_tc.cu)
+bool tc_propagate_supported(const PropArgs& a);
+int launch_propagate_tc(const PropArgs& a, cudaStream_t st);
+
 // tensor-core (tcgen05) one-hidden-layer MLP over particle rows (tc_mlp.cu)
 bool tc_mlp_supported(const psvo_mlp& net);
 int launch_particle_mlp_tc(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, float* out,
