@@ -56,7 +56,7 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
     s.a1_hi[g] = PSVO_TAKE(128 * 16 * 2); s.a1_lo[g] = PSVO_TAKE(128 * 16 * 2);
     s.a2_hi[g] = PSVO_TAKE(128 * kTcChunk * 2); s.a2_lo[g] = PSVO_TAKE(128 * kTcChunk * 2);
   }
-  s.bars = PSVO_TAKE(2 * kTcGroups * 8); s.slot = PSVO_TAKE(16);
+  s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);
 #undef PSVO_TAKE
   s.total = o;
   return s;
@@ -64,9 +64,9 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
 
 struct TcGroup {
   unsigned char *pa1h, *pa1l, *pa2h, *pa2l;
-  uint64_t *full, *done;
-  uint32_t phase;                  // parity of the next done[g] completion
-  uint32_t tD1, tD2q, tD2g;        // TMEM addresses (lane base included)
+  uint64_t *full, *dD1, *dA2;      // dD1[0..1]: L1 into D1 buffer b complete ; dA2: L2 complete (A2 reusable)
+  uint32_t par;                    // parities of the next completions: bit 0/1 = D1 buffer 0/1, bit 2 = A2
+  uint32_t tD1, tD2q, tD2g;        // TMEM addresses (lane base included); D1 buffers at tD1 and tD1 + 32
   int gt;                          // thread index within the group
 };
 
@@ -87,13 +87,17 @@ __device__ __forceinline__ void tc_stage_row(const TcGroup& g, const float (&x)[
   tc::mbar_arrive(g.full);
 }
 
-// compute-group side of one network: on return the accumulator D2 is complete
+// compute-group side of one network: on return the accumulator D2 is complete.
+// D1 is double buffered in TMEM, so L1(c+1) was issued a full stage before it is needed; the only wait on the
+// critical path is "L2(c-1) has finished reading A2", and it is placed AFTER the register work of chunk c.
 __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restrict__ sb1, int nchunk) {
   for (int c = 0; c < nchunk; ++c) {
-    tc::mbar_wait(g.done, g.phase); g.phase ^= 1;      // L1(c) complete; L2(c-1) complete -> A2 reusable
+    const int buf = c & 1;
+    tc::mbar_wait(g.dD1 + buf, (g.par >> buf) & 1u); g.par ^= 1u << buf;   // L1(c) complete
     tc::fence_after_sync();
     float v[32];
-    tc::tmem_ld32(g.tD1, v);
+    tc::tmem_ld32(g.tD1 + buf * 32, v);
+    uint4 hi[4], lo[4];
 #pragma unroll
     for (int kg = 0; kg < 4; ++kg) {
       float h[8];
@@ -103,16 +107,19 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restri
       h[2] = fmaxf(fmaf(v[kg * 8 + 2], kWUnscale, ba.z), 0.f); h[3] = fmaxf(fmaf(v[kg * 8 + 3], kWUnscale, ba.w), 0.f);
       h[4] = fmaxf(fmaf(v[kg * 8 + 4], kWUnscale, bb.x), 0.f); h[5] = fmaxf(fmaf(v[kg * 8 + 5], kWUnscale, bb.y), 0.f);
       h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
-      uint4 hi, lo;
-      tc::split8_f16(h, hi, lo);
-      *reinterpret_cast<uint4*>(g.pa2h + kg * 2048 + g.gt * 16) = hi;
-      *reinterpret_cast<uint4*>(g.pa2l + kg * 2048 + g.gt * 16) = lo;
+      tc::split8_f16(h, hi[kg], lo[kg]);
+    }
+    if (c > 0) { tc::mbar_wait(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u; }   // L2(c-1) complete -> A2 reusable
+#pragma unroll
+    for (int kg = 0; kg < 4; ++kg) {
+      *reinterpret_cast<uint4*>(g.pa2h + kg * 2048 + g.gt * 16) = hi[kg];
+      *reinterpret_cast<uint4*>(g.pa2l + kg * 2048 + g.gt * 16) = lo[kg];
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     tc::mbar_arrive(g.full);
   }
-  tc::mbar_wait(g.done, g.phase); g.phase ^= 1;        // L2(last) complete
+  tc::mbar_wait(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u;                   // L2(last) complete
   tc::fence_after_sync();
 }
 
@@ -121,27 +128,39 @@ struct TcNetDesc { uint64_t w1h, w1l, w2h, w2l; uint32_t idesc2; int NP; };
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// issue the MMAs of stage s of a network for one group (single thread)
-__device__ __forceinline__ void tc_issue_stage(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t a2h, uint64_t a2l,
-                                               uint32_t tD1, uint32_t tD2, int s, int nchunk) {
+__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint32_t tD1buf, int c) {
   const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
-  if (s > 0) {                                         // L2(s-1): K = 32 -> two K-steps
-    const int c = s - 1;
-#pragma unroll
-    for (int ks = 0; ks < kTcChunk / 16; ++ks) {
-      const uint32_t boff = (uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(nd.NP * 16);
-      const uint64_t ah = desc_add(a2h, ks * 4096), al = desc_add(a2l, ks * 4096);
-      const uint64_t bh = desc_add(nd.w2h, boff), bl = desc_add(nd.w2l, boff);
-      tc::mma_bf16(tD2, ah, bh, nd.idesc2, (c > 0) || (ks > 0));
-      tc::mma_bf16(tD2, ah, bl, nd.idesc2, true);
-      tc::mma_bf16(tD2, al, bh, nd.idesc2, true);
-    }
+  const uint64_t bh = desc_add(nd.w1h, c * (kTcChunk * 16)), bl = desc_add(nd.w1l, c * (kTcChunk * 16));
+  tc::mma_bf16(tD1buf, a1h, bh, idesc1, false);
+  tc::mma_bf16(tD1buf, a1h, bl, idesc1, true);
+  tc::mma_bf16(tD1buf, a1l, bh, idesc1, true);
+}
+
+// issue the MMAs of stage s of a network for one group (single thread):
+//   s = 0 : L1(0) -> D1[0], L1(1) -> D1[1]           s >= 1 : L2(s-1) ; L1(s+1) -> D1[(s+1)&1]
+__device__ __forceinline__ void tc_issue_stage(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t a2h, uint64_t a2l,
+                                               uint32_t tD1, uint32_t tD2, int s, int nchunk, uint64_t* dD1, uint64_t* dA2) {
+  if (s == 0) {
+    tc_issue_l1(nd, a1h, a1l, tD1, 0);
+    tc::mma_commit(dD1);
+    if (nchunk > 1) { tc_issue_l1(nd, a1h, a1l, tD1 + 32, 1); tc::mma_commit(dD1 + 1); }
+    return;
   }
-  if (s < nchunk) {                                    // L1(s)
-    const uint64_t bh = desc_add(nd.w1h, s * (kTcChunk * 16)), bl = desc_add(nd.w1l, s * (kTcChunk * 16));
-    tc::mma_bf16(tD1, a1h, bh, idesc1, false);
-    tc::mma_bf16(tD1, a1h, bl, idesc1, true);
-    tc::mma_bf16(tD1, a1l, bh, idesc1, true);
+  const int c = s - 1;                                 // L2(c): K = 32 -> two K-steps
+#pragma unroll
+  for (int ks = 0; ks < kTcChunk / 16; ++ks) {
+    const uint32_t boff = (uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(nd.NP * 16);
+    const uint64_t ah = desc_add(a2h, ks * 4096), al = desc_add(a2l, ks * 4096);
+    const uint64_t bh = desc_add(nd.w2h, boff), bl = desc_add(nd.w2l, boff);
+    tc::mma_bf16(tD2, ah, bh, nd.idesc2, (c > 0) || (ks > 0));
+    tc::mma_bf16(tD2, ah, bl, nd.idesc2, true);
+    tc::mma_bf16(tD2, al, bh, nd.idesc2, true);
+  }
+  tc::mma_commit(dA2);
+  if (s + 1 < nchunk) {
+    const int b = (s + 1) & 1;
+    tc_issue_l1(nd, a1h, a1l, tD1 + b * 32, s + 1);
+    tc::mma_commit(dD1 + b);
   }
 }
 
@@ -161,8 +180,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);
-  uint64_t* done = full + kTcGroups;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g]
+  uint64_t* dD1 = full + kTcGroups;                              // [g][2]
+  uint64_t* dA2 = dD1 + 2 * kTcGroups;                           // [g]
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
   // ---- stage weights (fp16 hi/lo, UMMA B layout, pre-scaled), biases, constants
@@ -184,7 +204,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
-  if (tid < kTcGroups) { tc::mbar_init(full + tid, 128); tc::mbar_init(done + tid, 1); }
+  if (tid < kTcGroups) { tc::mbar_init(full + tid, 128); tc::mbar_init(dD1 + 2 * tid, 1); tc::mbar_init(dD1 + 2 * tid + 1, 1); tc::mbar_init(dA2 + tid, 1); }
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -234,15 +254,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
             const int within = step[g] % (NN * S);
             const bool is_g = t0 || within >= S;
             const int s = is_g && !t0 ? within - S : within;
-            const uint32_t tD1 = tmem + g * 128, tD2 = tmem + g * 128 + (is_g ? 64 : 32);
-            tc_issue_stage(is_g ? ng : nq, a1h[g], a1l[g], a2h[g], a2l[g], tD1, tD2, s, nchunk);
-            tc::mma_commit(done + g);
+            const uint32_t tD1 = tmem + g * 128, tD2 = tmem + g * 128 + (is_g ? 96 : 64);
+            tc_issue_stage(is_g ? ng : nq, a1h[g], a1l[g], a2h[g], a2l[g], tD1, tD2, s, nchunk, dD1 + 2 * g, dA2 + g);
           }
           __syncwarp();
           step[g]++; remaining--;
         }
       }
-      if (remaining == before) __nanosleep(40);        // nothing was ready: leave the issue slots to the compute warps
+      (void)before;
     }
   } else {
     // =================================== compute groups ===================================
@@ -255,10 +274,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     (void)s1;
     TcGroup g;
     g.gt = tid & 127;
-    g.full = full + grp; g.done = done + grp; g.phase = 0;
+    g.full = full + grp; g.dD1 = dD1 + 2 * grp; g.dA2 = dA2 + grp; g.par = 0;
     g.pa1h = sm + L.a1_hi[grp]; g.pa1l = sm + L.a1_lo[grp]; g.pa2h = sm + L.a2_hi[grp]; g.pa2l = sm + L.a2_lo[grp];
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128 + lane_base; g.tD2q = tmem + grp * 128 + 32 + lane_base; g.tD2g = tmem + grp * 128 + 64 + lane_base;
+    g.tD1 = tmem + grp * 128 + lane_base; g.tD2q = tmem + grp * 128 + 64 + lane_base; g.tD2g = tmem + grp * 128 + 96 + lane_base;
 
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const int b = wi / tiles_per_seq;
