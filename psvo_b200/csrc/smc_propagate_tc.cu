@@ -401,7 +401,7 @@ bool tc_propagate_supported(const PropArgs& a) {
 
 int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
   const int H = a.g.width[0];
-  const int NPG = a.Dy <= 16 ? 16 : 32;
+  const int NPG = 32;      // one instantiation: the emission head is padded to 32 outputs
   const TcPropSmem L = tc_prop_layout(H, NPG);
   const size_t smem = L.total + 128;
   PSVO_REQUIRE(smem <= 227 * 1024, "tensor-core propagate: %zu B of shared memory", smem);
@@ -409,11 +409,7 @@ int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
   int grid = (tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
   ProfScope ps_(PK_PROP, st);
-  if (NPG == 16) {
-    static bool cfg = false;
-    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
-    smc_propagate_tc_kernel<16><<<grid, kTcThreads, smem, st>>>(a);
-  } else {
+  {
     static bool cfg = false;
     if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
     smc_propagate_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(a);
