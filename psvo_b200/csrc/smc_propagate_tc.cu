@@ -93,7 +93,7 @@ __device__ __forceinline__ void tc_stage_row(const TcGroup& g, const float (&x)[
 __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restrict__ sb1, int nchunk) {
   for (int c = 0; c < nchunk; ++c) {
     const int buf = c & 1;
-    tc::mbar_wait(g.dD1 + buf, (g.par >> buf) & 1u); g.par ^= 1u << buf;   // L1(c) complete
+    tc::mbar_spin(g.dD1 + buf, (g.par >> buf) & 1u); g.par ^= 1u << buf;   // L1(c) complete
     tc::fence_after_sync();
     float v[32];
     tc::tmem_ld32(g.tD1 + buf * 32, v);
@@ -109,7 +109,7 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restri
       h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
       tc::split8_f16(h, hi[kg], lo[kg]);
     }
-    if (c > 0) { tc::mbar_wait(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u; }   // L2(c-1) complete -> A2 reusable
+    if (c > 0) { tc::mbar_spin(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u; }   // L2(c-1) complete -> A2 reusable
 #pragma unroll
     for (int kg = 0; kg < 4; ++kg) {
       *reinterpret_cast<uint4*>(g.pa2h + kg * 2048 + g.gt * 16) = hi[kg];
@@ -119,7 +119,7 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restri
     tc::fence_before_sync();
     tc::mbar_arrive(g.full);
   }
-  tc::mbar_wait(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u;                   // L2(last) complete
+  tc::mbar_spin(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u;                   // L2(last) complete
   tc::fence_after_sync();
 }
 

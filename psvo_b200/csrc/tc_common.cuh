@@ -118,6 +118,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
 }
+// pure polling wait (no hardware sleep): lowest wake-up latency, costs issue slots while waiting
+__device__ __forceinline__ void mbar_spin(uint64_t* mbar, uint32_t parity) {
+  while (!mbar_test(mbar, parity)) {}
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
