@@ -7,18 +7,17 @@
 // Shape of the work (BASELINE config 5: Dx=16, Dy=32, H=256): per particle-step 41 kFLOP of tiny-K GEMMs
 //   [128 x 16] x [16 x 256] -> relu -> [128 x 256] x [256 x 16|32].
 //
-// Warp-specialised CTA: 4 compute groups of 128 threads + 1 MMA-issuing warp.
-//   compute group : owns one 128-particle tile at a time (TMEM lane == row == thread).  Per network it walks the
-//                   hidden layer in chunks of 32 units: wait done[g] -> tcgen05.ld its D1 row -> scale + bias ->
-//                   ReLU -> fp16 hi/lo split -> 16-byte stores into the A2 operand -> fence.proxy.async ->
-//                   mbarrier.arrive full[g].  No block-level barrier anywhere in the loop.
-//   MMA warp      : polls the four full[g] barriers round-robin; when a group's operand is staged it issues that
-//                   group's next MMAs (one elected lane) and tcgen05.commit's onto done[g]:
-//                       stage 0      : L1(0)              D1[128x32]  = A1 * W1[0]^T        3 MMAs, K = 16
-//                       stage s      : L2(s-1), L1(s)     D2[128xNP] += A2 * W2[s-1]^T      2 K-steps x 3 MMAs
-//                       stage nchunk : L2(nchunk-1)
-//   While one group waits for its MMAs the other three keep the CUDA cores busy; all groups share the staged
-//   fp16 weights (80 KB at H = 256).
+// CTA = 4 independent groups of 128 threads; a group owns one 128-particle tile at a time (TMEM lane == row ==
+// thread) and walks the hidden layer of each network in chunks of 32 units:
+//     threads      : wait L1(c) -> tcgen05.ld the D1 row -> scale + bias -> ReLU -> fp16 hi/lo split (registers)
+//                    -> wait L2(c-1) -> 16-byte stores into the A2 operand -> fence.proxy.async -> group barrier
+//     warp 0, 1    : L2(c), one K-step of 16 each, into two separate accumulators D2a / D2b  (3 MMAs each)
+//     warp 2       : L1(c+2) into the D1 buffer that chunk c just released                    (3 MMAs)
+// A single thread can issue one tcgen05.mma per ~161 cycles however small the tile is (profiles/microbench), so
+// the 144 tiny-K MMAs of a tile are spread over three issuing warps per group (twelve per CTA); D1 is double
+// buffered in TMEM so L1 runs two chunks ahead, and the wait for L2(c-1) sits after the register work of chunk c.
+// While a group waits, the other three groups keep the CUDA cores busy; all groups share the staged fp16
+// weights (80 KB at H = 256).
 // Arithmetic ("fp16x3"): x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits); a*w is evaluated as
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM; weights are pre-scaled by 2^8 (exact) so that
 // their lo halves stay in fp16's normal range, and the scale is undone inside the bias FFMA.  Operands must stay
@@ -32,7 +31,7 @@ namespace psvo {
 
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
-constexpr int kTcThreads = kTcGroups * 128 + 32;
+constexpr int kTcThreads = kTcGroups * 128;
 constexpr float kWScale = 256.0f, kWUnscale = 1.0f / 256.0f;
 
 struct TcPropSmem {
@@ -62,16 +61,56 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   return s;
 }
 
+struct TcNetDesc { uint64_t w1h, w1l, w2h, w2l; uint32_t idesc2; int NP; };
+
 struct TcGroup {
   unsigned char *pa1h, *pa1l, *pa2h, *pa2l;
-  uint64_t *full, *dD1, *dA2;      // dD1[0..1]: L1 into D1 buffer b complete ; dA2: L2 complete (A2 reusable)
-  uint32_t par;                    // parities of the next completions: bit 0/1 = D1 buffer 0/1, bit 2 = A2
-  uint32_t tD1, tD2q, tD2g;        // TMEM addresses (lane base included); D1 buffers at tD1 and tD1 + 32
-  int gt;                          // thread index within the group
+  uint64_t a1h, a1l, a2h, a2l;     // UMMA descriptors of this group's A operands
+  uint64_t *mD1, *mL2;             // mD1[0..1]: L1 into D1 buffer b complete ; mL2[0..1]: L2 half a/b complete
+  uint32_t par;                    // parities of the next completions: bit 0/1 = D1 buffers, bit 2/3 = L2 halves
+  uint32_t tD1, tD2;               // TMEM column bases of the group (no lane offset): D1[0], D1[1] = +32 ; D2a, D2b = +32
+  uint32_t lane_base;
+  int gt, gw, lane;                // thread / warp index within the group, lane
+  int bar_id;
 };
 
-// stage this thread's 16-wide row as the A operand of layer 1 and hand it to the MMA warp
-__device__ __forceinline__ void tc_stage_row(const TcGroup& g, const float (&x)[16]) {
+__device__ __forceinline__ void group_sync(const TcGroup& g) {
+  asm volatile("bar.sync %0, 128;\n" :: "r"(g.bar_id) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+// L1(c): D1[buf] = A1 * W1[c]^T   (3 MMAs, single thread)
+__device__ __forceinline__ void tc_issue_l1(const TcGroup& g, const TcNetDesc& nd, int c) {
+  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
+  const uint32_t d = g.tD1 + (c & 1) * 32;
+  const uint64_t bh = desc_add(nd.w1h, c * (kTcChunk * 16)), bl = desc_add(nd.w1l, c * (kTcChunk * 16));
+  tc::mma_bf16(d, g.a1h, bh, idesc1, false);
+  tc::mma_bf16(d, g.a1h, bl, idesc1, true);
+  tc::mma_bf16(d, g.a1l, bh, idesc1, true);
+  tc::mma_commit(g.mD1 + (c & 1));
+}
+// half `ks` of L2(c): D2[ks] += A2[:, 16ks:16ks+16] * W2[c, ks]^T   (3 MMAs, single thread)
+__device__ __forceinline__ void tc_issue_l2(const TcGroup& g, const TcNetDesc& nd, int c, int ks) {
+  const uint32_t boff = (uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(nd.NP * 16);
+  const uint64_t ah = desc_add(g.a2h, ks * 4096), al = desc_add(g.a2l, ks * 4096);
+  const uint64_t bh = desc_add(nd.w2h, boff), bl = desc_add(nd.w2l, boff);
+  const uint32_t d = g.tD2 + ks * 32;
+  tc::mma_bf16(d, ah, bh, nd.idesc2, c > 0);
+  tc::mma_bf16(d, ah, bl, nd.idesc2, true);
+  tc::mma_bf16(d, al, bh, nd.idesc2, true);
+  tc::mma_commit(g.mL2 + ks);
+}
+
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par, int bit) {
+  tc::mbar_wait(bar, (par >> bit) & 1u);
+  par ^= 1u << bit;
+}
+
+// One network for the group's current tile: x = this thread's input row.  On return the two accumulators
+// D2a (g.tD2) and D2b (g.tD2 + 32) are complete; their sum is W2^T relu(W1^T x + b1) * kWScale^... (see caller).
+__device__ __forceinline__ void tc_mlp_group(TcGroup& g, const TcNetDesc& nd, const float (&x)[16],
+                                             const float* __restrict__ sb1, int nchunk) {
+  // ---- stage the A operand of layer 1
 #pragma unroll
   for (int kg = 0; kg < 2; ++kg) {
     float v[8];
@@ -83,20 +122,20 @@ __device__ __forceinline__ void tc_stage_row(const TcGroup& g, const float (&x)[
     *reinterpret_cast<uint4*>(g.pa1l + kg * 2048 + g.gt * 16) = lo;
   }
   tc::fence_proxy_async();
-  tc::fence_before_sync();           // orders this thread's earlier tcgen05.ld (previous accumulator reads)
-  tc::mbar_arrive(g.full);
-}
+  tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
+  group_sync(g);
+  if (g.lane == 0 && (g.gw == 2 || g.gw == 3)) {     // L1(0) by warp 2, L1(1) by warp 3
+    tc::fence_after_sync();
+    const int c = g.gw - 2;
+    if (c < nchunk) tc_issue_l1(g, nd, c);
+  }
+  __syncwarp();
 
-// compute-group side of one network: on return the accumulator D2 is complete.
-// D1 is double buffered in TMEM, so L1(c+1) was issued a full stage before it is needed; the only wait on the
-// critical path is "L2(c-1) has finished reading A2", and it is placed AFTER the register work of chunk c.
-__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restrict__ sb1, int nchunk) {
   for (int c = 0; c < nchunk; ++c) {
-    const int buf = c & 1;
-    tc::mbar_spin(g.dD1 + buf, (g.par >> buf) & 1u); g.par ^= 1u << buf;   // L1(c) complete
+    tc_wait(g.mD1 + (c & 1), g.par, c & 1);                               // L1(c) complete
     tc::fence_after_sync();
     float v[32];
-    tc::tmem_ld32(g.tD1 + buf * 32, v);
+    tc::tmem_ld32(g.tD1 + g.lane_base + (c & 1) * 32, v);
     uint4 hi[4], lo[4];
 #pragma unroll
     for (int kg = 0; kg < 4; ++kg) {
@@ -109,7 +148,7 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restri
       h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
       tc::split8_f16(h, hi[kg], lo[kg]);
     }
-    if (c > 0) { tc::mbar_spin(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u; }   // L2(c-1) complete -> A2 reusable
+    if (c > 0) { tc_wait(g.mL2, g.par, 2); tc_wait(g.mL2 + 1, g.par, 3); }   // L2(c-1) complete -> A2 reusable
 #pragma unroll
     for (int kg = 0; kg < 4; ++kg) {
       *reinterpret_cast<uint4*>(g.pa2h + kg * 2048 + g.gt * 16) = hi[kg];
@@ -117,51 +156,16 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float* __restri
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
-    tc::mbar_arrive(g.full);
+    group_sync(g);                                                         // A2(c) staged, D1[c&1] released
+    if (g.lane == 0 && g.gw < 3) {
+      tc::fence_after_sync();
+      if (g.gw < 2) tc_issue_l2(g, nd, c, g.gw);
+      else if (c + 2 < nchunk) tc_issue_l1(g, nd, c + 2);
+    }
+    __syncwarp();
   }
-  tc::mbar_spin(g.dA2, (g.par >> 2) & 1u); g.par ^= 4u;                   // L2(last) complete
+  tc_wait(g.mL2, g.par, 2); tc_wait(g.mL2 + 1, g.par, 3);                  // L2(last) complete
   tc::fence_after_sync();
-}
-
-// MMA-warp side: descriptors of one network
-struct TcNetDesc { uint64_t w1h, w1l, w2h, w2l; uint32_t idesc2; int NP; };
-
-__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
-
-__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint32_t tD1buf, int c) {
-  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
-  const uint64_t bh = desc_add(nd.w1h, c * (kTcChunk * 16)), bl = desc_add(nd.w1l, c * (kTcChunk * 16));
-  tc::mma_bf16(tD1buf, a1h, bh, idesc1, false);
-  tc::mma_bf16(tD1buf, a1h, bl, idesc1, true);
-  tc::mma_bf16(tD1buf, a1l, bh, idesc1, true);
-}
-
-// issue the MMAs of stage s of a network for one group (single thread):
-//   s = 0 : L1(0) -> D1[0], L1(1) -> D1[1]           s >= 1 : L2(s-1) ; L1(s+1) -> D1[(s+1)&1]
-__device__ __forceinline__ void tc_issue_stage(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t a2h, uint64_t a2l,
-                                               uint32_t tD1, uint32_t tD2, int s, int nchunk, uint64_t* dD1, uint64_t* dA2) {
-  if (s == 0) {
-    tc_issue_l1(nd, a1h, a1l, tD1, 0);
-    tc::mma_commit(dD1);
-    if (nchunk > 1) { tc_issue_l1(nd, a1h, a1l, tD1 + 32, 1); tc::mma_commit(dD1 + 1); }
-    return;
-  }
-  const int c = s - 1;                                 // L2(c): K = 32 -> two K-steps
-#pragma unroll
-  for (int ks = 0; ks < kTcChunk / 16; ++ks) {
-    const uint32_t boff = (uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(nd.NP * 16);
-    const uint64_t ah = desc_add(a2h, ks * 4096), al = desc_add(a2l, ks * 4096);
-    const uint64_t bh = desc_add(nd.w2h, boff), bl = desc_add(nd.w2l, boff);
-    tc::mma_bf16(tD2, ah, bh, nd.idesc2, (c > 0) || (ks > 0));
-    tc::mma_bf16(tD2, ah, bl, nd.idesc2, true);
-    tc::mma_bf16(tD2, al, bh, nd.idesc2, true);
-  }
-  tc::mma_commit(dA2);
-  if (s + 1 < nchunk) {
-    const int b = (s + 1) & 1;
-    tc_issue_l1(nd, a1h, a1l, tD1 + b * 32, s + 1);
-    tc::mma_commit(dD1 + b);
-  }
 }
 
 template <int NPG>
@@ -180,9 +184,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g]
-  uint64_t* dD1 = full + kTcGroups;                              // [g][2]
-  uint64_t* dA2 = dD1 + 2 * kTcGroups;                           // [g]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][4]: mD1[0], mD1[1], mL2[0], mL2[1]
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
   // ---- stage weights (fp16 hi/lo, UMMA B layout, pre-scaled), biases, constants
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
-  if (tid < kTcGroups) { tc::mbar_init(full + tid, 128); tc::mbar_init(dD1 + 2 * tid, 1); tc::mbar_init(dD1 + 2 * tid + 1, 1); tc::mbar_init(dA2 + tid, 1); }
+  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, 1);
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -221,49 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const int tiles_per_seq = (N + 127) / 128;
   const int work = a.B * tiles_per_seq;
 
-  if (warp == kTcGroups * 4) {
-    // =================================== MMA-issuing warp ===================================
-    TcNetDesc nq, ng;
-    nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-    nq.w2h = tc::make_desc(tc::smem_u32(sm + L.w2q_hi), 16 * 16, 128); nq.w2l = tc::make_desc(tc::smem_u32(sm + L.w2q_lo), 16 * 16, 128);
-    nq.idesc2 = tc::make_idesc_f16(128, 16); nq.NP = 16;
-    ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-    ng.w2h = tc::make_desc(tc::smem_u32(sm + L.w2g_hi), NPG * 16, 128); ng.w2l = tc::make_desc(tc::smem_u32(sm + L.w2g_lo), NPG * 16, 128);
-    ng.idesc2 = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
-    const int S = nchunk + 1;                         // stages per network
-    const int NN = t0 ? 1 : 2;                        // networks per tile (q1 is skipped at t = 0)
-    int step[kTcGroups], nsteps[kTcGroups];
-    uint64_t a1h[kTcGroups], a1l[kTcGroups], a2h[kTcGroups], a2l[kTcGroups];
-    int remaining = 0;
-#pragma unroll
-    for (int g = 0; g < kTcGroups; ++g) {
-      const int first = blockIdx.x * kTcGroups + g;
-      const int ntile = first < work ? (work - first + gridDim.x * kTcGroups - 1) / (gridDim.x * kTcGroups) : 0;
-      step[g] = 0; nsteps[g] = ntile * NN * S;
-      remaining += nsteps[g];
-      a1h[g] = tc::make_desc(tc::smem_u32(sm + L.a1_hi[g]), 2048, 128); a1l[g] = tc::make_desc(tc::smem_u32(sm + L.a1_lo[g]), 2048, 128);
-      a2h[g] = tc::make_desc(tc::smem_u32(sm + L.a2_hi[g]), 2048, 128); a2l[g] = tc::make_desc(tc::smem_u32(sm + L.a2_lo[g]), 2048, 128);
-    }
-    while (remaining > 0) {
-      const int before = remaining;
-#pragma unroll
-      for (int g = 0; g < kTcGroups; ++g) {
-        if (step[g] < nsteps[g] && tc::mbar_test(full + g, (uint32_t)(step[g] & 1))) {
-          tc::fence_after_sync();
-          if (lane == 0) {
-            const int within = step[g] % (NN * S);
-            const bool is_g = t0 || within >= S;
-            const int s = is_g && !t0 ? within - S : within;
-            const uint32_t tD1 = tmem + g * 128, tD2 = tmem + g * 128 + (is_g ? 96 : 64);
-            tc_issue_stage(is_g ? ng : nq, a1h[g], a1l[g], a2h[g], a2l[g], tD1, tD2, s, nchunk, dD1 + 2 * g, dA2 + g);
-          }
-          __syncwarp();
-          step[g]++; remaining--;
-        }
-      }
-      (void)before;
-    }
-  } else {
+  {
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
     const float* s1 = C; const float* sp = C + 16; const float* inv1 = C + 32; const float* inv2 = C + 48;
@@ -272,12 +232,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     const float neg_logN = -logf((float)N);
     (void)s1;
+    TcNetDesc nq, ng;
+    nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+    nq.w2h = tc::make_desc(tc::smem_u32(sm + L.w2q_hi), 16 * 16, 128); nq.w2l = tc::make_desc(tc::smem_u32(sm + L.w2q_lo), 16 * 16, 128);
+    nq.idesc2 = tc::make_idesc_f16(128, 16); nq.NP = 16;
+    ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+    ng.w2h = tc::make_desc(tc::smem_u32(sm + L.w2g_hi), NPG * 16, 128); ng.w2l = tc::make_desc(tc::smem_u32(sm + L.w2g_lo), NPG * 16, 128);
+    ng.idesc2 = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
     TcGroup g;
-    g.gt = tid & 127;
-    g.full = full + grp; g.dD1 = dD1 + 2 * grp; g.dA2 = dA2 + grp; g.par = 0;
+    g.gt = tid & 127; g.gw = warp & 3; g.lane = lane; g.bar_id = 1 + grp;
+    g.mD1 = bars + 4 * grp; g.mL2 = bars + 4 * grp + 2; g.par = 0;
     g.pa1h = sm + L.a1_hi[grp]; g.pa1l = sm + L.a1_lo[grp]; g.pa2h = sm + L.a2_hi[grp]; g.pa2l = sm + L.a2_lo[grp];
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128 + lane_base; g.tD2q = tmem + grp * 128 + 64 + lane_base; g.tD2g = tmem + grp * 128 + 96 + lane_base;
+    g.a1h = tc::make_desc(tc::smem_u32(g.pa1h), 2048, 128); g.a1l = tc::make_desc(tc::smem_u32(g.pa1l), 2048, 128);
+    g.a2h = tc::make_desc(tc::smem_u32(g.pa2h), 2048, 128); g.a2l = tc::make_desc(tc::smem_u32(g.pa2l), 2048, 128);
+    g.lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    g.tD1 = tmem + grp * 128; g.tD2 = tmem + grp * 128 + 64;
 
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const int b = wi / tiles_per_seq;
@@ -300,9 +269,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
 #pragma unroll
           for (int d = 0; d < 16; ++d) x[d] = d < Dx ? src[d] : 0.0f;
         }
-        tc_stage_row(g, x);
       }
-      // noise for this particle (independent of the MLP: issued while the tensor core works)
+      // noise for this particle
       float e[16];
       if (a.eps != nullptr) {
         const float* src = a.eps + row * Dx;
@@ -317,10 +285,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         }
       }
       if (!t0) {
-        tc_mlp_compute(g, sb1q, nchunk);
-        tc::tmem_ld16(g.tD2q, mu1);
+        tc_mlp_group(g, nq, x, sb1q, nchunk);
+        float mb[16];
+        tc::tmem_ld16(g.tD2 + g.lane_base, mu1);
+        tc::tmem_ld16(g.tD2 + g.lane_base + 32, mb);
 #pragma unroll
-        for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d], kWUnscale, sb2q[d]);
+        for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d] + mb[d], kWUnscale, sb2q[d]);
       } else {
 #pragma unroll
         for (int d = 0; d < 16; ++d) mu1[d] = d < Dx ? a.mu0[(size_t)b * Dx + d] : 0.0f;
@@ -355,19 +325,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       }
 
       // ---- emission
-      tc_stage_row(g, x);
-      tc_mlp_compute(g, sb1g, nchunk);
+      tc_mlp_group(g, ng, x, sb1g, nchunk);
       float gsum = 0.f;
 #pragma unroll
       for (int c = 0; c < NPG; c += 16) {
-        float mug[16];
-        tc::tmem_ld16(g.tD2g + c, mug);
+        float mug[16], mgb[16];
+        tc::tmem_ld16(g.tD2 + g.lane_base + c, mug);
+        tc::tmem_ld16(g.tD2 + g.lane_base + 32 + c, mgb);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int d = c + i;
           if (d < Dy) {
             const float y = a.obs[bt * Dy + d];
-            const float mu = fmaf(mug[i], kWUnscale, sb2g[d]);
+            const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
             const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
           }
