@@ -7,17 +7,18 @@
 // Shape of the work (BASELINE config 5: Dx=16, Dy=32, H=256): per particle-step 41 kFLOP of tiny-K GEMMs
 //   [128 x 16] x [16 x 256] -> relu -> [128 x 256] x [256 x 16|32].
 //
-// CTA = 4 independent groups of 128 threads; a group owns one 128-particle tile at a time (TMEM lane == row ==
-// thread) and walks the hidden layer of each network in chunks of 32 units:
-//     threads      : wait L1(c) -> tcgen05.ld the D1 row -> scale + bias -> ReLU -> fp16 hi/lo split (registers)
-//                    -> wait L2(c-1) -> 16-byte stores into the A2 operand -> fence.proxy.async -> group barrier
-//     warp 0, 1    : L2(c), one K-step of 16 each, into two separate accumulators D2a / D2b  (3 MMAs each)
-//     warp 2       : L1(c+2) into the D1 buffer that chunk c just released                    (3 MMAs)
-// A single thread can issue one tcgen05.mma per ~161 cycles however small the tile is (profiles/microbench), so
-// the 144 tiny-K MMAs of a tile are spread over three issuing warps per group (twelve per CTA); D1 is double
-// buffered in TMEM so L1 runs two chunks ahead, and the wait for L2(c-1) sits after the register work of chunk c.
-// While a group waits, the other three groups keep the CUDA cores busy; all groups share the staged fp16
-// weights (80 KB at H = 256).
+// CTA = 4 compute groups of 128 threads + 4 MMA-issuing warps (one per group).  A group owns one 128-particle tile
+// at a time (TMEM lane == row == thread) and walks the hidden layer of each network in chunks of 32 units:
+//     compute threads : wait L1(c) -> tcgen05.ld the D1 row -> scale + bias -> ReLU -> fp16 hi/lo split (registers)
+//                       -> wait L2(c-1) -> 16-byte stores into the A2 operand -> fence.proxy.async ->
+//                       mbarrier.arrive full[g]          (no block- or group-wide barrier in the loop)
+//     MMA warp g      : wait full[g] -> L2(c) (2 K-steps x 2 MMAs) -> commit ; L1(c+2) (3 MMAs) -> commit
+// D1 is double buffered in TMEM so L1 runs two chunks ahead of the epilogue, and the wait for L2(c-1) sits after the
+// register work of chunk c, so the compute warps only ever stall when the tensor pipe is the bottleneck.
+// Measured cost model (profiles/microbench): a K=16 tcgen05.mma occupies the tensor pipe for max(40, N/2) cycles
+// whatever its size, so MMAs are made as wide as TMEM allows: the layer-2 weights are stacked [w_hi ; w_lo] along N,
+// which turns hi*hi + hi*lo into ONE instruction (the two halves of the accumulator are added in the epilogue).
+// All groups share the staged fp16 weights (80 KB at H = 256).
 // Arithmetic ("fp16x3"): x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits); a*w is evaluated as
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM; weights are pre-scaled by 2^8 (exact) so that
 // their lo halves stay in fp16's normal range, and the scale is undone inside the bias FFMA.  Operands must stay
@@ -31,11 +32,11 @@ namespace psvo {
 
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
-constexpr int kTcThreads = kTcGroups * 128;
+constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
 constexpr float kWScale = 256.0f, kWUnscale = 1.0f / 256.0f;
 
 struct TcPropSmem {
-  uint32_t w1q_hi, w1q_lo, w2q_hi, w2q_lo, w1g_hi, w1g_lo, w2g_hi, w2g_lo;   // fp16 weights (B operands)
+  uint32_t w1q_hi, w1q_lo, w2q, w1g_hi, w1g_lo, w2g;   // fp16 weights (B operands); w2*: [K-group][hi rows | lo rows]
   uint32_t b1q, b2q, b1g, b2g, consts;                                        // fp32
   uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups], a2_hi[kTcGroups], a2_lo[kTcGroups];
   uint32_t bars, slot, total;
@@ -46,71 +47,73 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   uint32_t o = 0;
 #define PSVO_TAKE(bytes) (o += (((bytes) + 127u) & ~127u), o - (((bytes) + 127u) & ~127u))
   s.w1q_hi = PSVO_TAKE(H * 16 * 2); s.w1q_lo = PSVO_TAKE(H * 16 * 2);
-  s.w2q_hi = PSVO_TAKE(16 * H * 2); s.w2q_lo = PSVO_TAKE(16 * H * 2);
+  s.w2q = PSVO_TAKE(2 * 16 * H * 2);
   s.w1g_hi = PSVO_TAKE(H * 16 * 2); s.w1g_lo = PSVO_TAKE(H * 16 * 2);
-  s.w2g_hi = PSVO_TAKE(NPG * H * 2); s.w2g_lo = PSVO_TAKE(NPG * H * 2);
+  s.w2g = PSVO_TAKE(2 * NPG * H * 2);
   s.b1q = PSVO_TAKE(H * 4); s.b2q = PSVO_TAKE(16 * 4); s.b1g = PSVO_TAKE(H * 4); s.b2g = PSVO_TAKE(32 * 4);
   s.consts = PSVO_TAKE(160 * 4);
   for (int g = 0; g < kTcGroups; ++g) {
     s.a1_hi[g] = PSVO_TAKE(128 * 16 * 2); s.a1_lo[g] = PSVO_TAKE(128 * 16 * 2);
     s.a2_hi[g] = PSVO_TAKE(128 * kTcChunk * 2); s.a2_lo[g] = PSVO_TAKE(128 * kTcChunk * 2);
   }
-  s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);
+  s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full, mD1[0], mD1[1], mL2
 #undef PSVO_TAKE
   s.total = o;
   return s;
 }
 
-struct TcNetDesc { uint64_t w1h, w1l, w2h, w2l; uint32_t idesc2; int NP; };
+struct TcNetDesc { uint64_t w1h, w1l, w2; uint32_t idesc2a, idesc2b; int NP; };
 
 struct TcGroup {
-  unsigned char *pa1h, *pa1l, *pa2h, *pa2l;
-  uint64_t a1h, a1l, a2h, a2l;     // UMMA descriptors of this group's A operands
-  uint64_t *mD1, *mL2;             // mD1[0..1]: L1 into D1 buffer b complete ; mL2[0..1]: L2 half a/b complete
-  uint32_t par;                    // parities of the next completions: bit 0/1 = D1 buffers, bit 2/3 = L2 halves
-  uint32_t tD1, tD2;               // TMEM column bases of the group (no lane offset): D1[0], D1[1] = +32 ; D2a, D2b = +32
-  uint32_t lane_base;
-  int gt, gw, lane;                // thread / warp index within the group, lane
-  int bar_id;
+  unsigned char *pa2h, *pa2l;      // this thread's 16-byte slot in the A2 operand (K-group 0)
+  unsigned char *pa1h, *pa1l;      // same for A1
+  uint64_t *full, *mD1, *mL2;      // full: operand staged (128 arrivals) ; mD1[0..1]: L1 into D1 buffer done ; mL2: L2 done
+  uint32_t par;                    // parities of the next completions: bit 0/1 = mD1[0/1], bit 2 = mL2
+  uint32_t tD1, tD2;               // TMEM addresses incl. this warp's lane offset: D1[1] = tD1 + 32 ; D2 = 2*NP columns
 };
 
-__device__ __forceinline__ void group_sync(const TcGroup& g) {
-  asm volatile("bar.sync %0, 128;\n" :: "r"(g.bar_id) : "memory");
-}
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// L1(c): D1[buf] = A1 * W1[c]^T   (3 MMAs, single thread)
-__device__ __forceinline__ void tc_issue_l1(const TcGroup& g, const TcNetDesc& nd, int c) {
-  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
-  const uint32_t d = g.tD1 + (c & 1) * 32;
-  const uint64_t bh = desc_add(nd.w1h, c * (kTcChunk * 16)), bl = desc_add(nd.w1l, c * (kTcChunk * 16));
-  tc::mma_bf16(d, g.a1h, bh, idesc1, false);
-  tc::mma_bf16(d, g.a1h, bl, idesc1, true);
-  tc::mma_bf16(d, g.a1l, bh, idesc1, true);
-  tc::mma_commit(g.mD1 + (c & 1));
-}
-// half `ks` of L2(c): D2[ks] += A2[:, 16ks:16ks+16] * W2[c, ks]^T   (3 MMAs, single thread)
-__device__ __forceinline__ void tc_issue_l2(const TcGroup& g, const TcNetDesc& nd, int c, int ks) {
-  const uint32_t boff = (uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(nd.NP * 16);
-  const uint64_t ah = desc_add(g.a2h, ks * 4096), al = desc_add(g.a2l, ks * 4096);
-  const uint64_t bh = desc_add(nd.w2h, boff), bl = desc_add(nd.w2l, boff);
-  const uint32_t d = g.tD2 + ks * 32;
-  tc::mma_bf16(d, ah, bh, nd.idesc2, c > 0);
-  tc::mma_bf16(d, ah, bl, nd.idesc2, true);
-  tc::mma_bf16(d, al, bh, nd.idesc2, true);
-  tc::mma_commit(g.mL2 + ks);
+template <int BIT>
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
+  tc::mbar_wait(bar, (par >> BIT) & 1u);
+  par ^= 1u << BIT;
 }
 
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par, int bit) {
-  tc::mbar_wait(bar, (par >> bit) & 1u);
-  par ^= 1u << bit;
+// hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> scale + bias -> ReLU -> fp16 hi/lo -> A2 -> arrive
+template <int BUF>
+__device__ __forceinline__ void tc_chunk(TcGroup& g, const float* __restrict__ sb1, int c) {
+  tc_wait<BUF>(g.mD1 + BUF, g.par);                                       // L1(c) complete
+  tc::fence_after_sync();
+  float v[32];
+  tc::tmem_ld32(g.tD1 + BUF * 32, v);
+  uint4 hi[4], lo[4];
+  const float* bias = sb1 + c * kTcChunk;
+#pragma unroll
+  for (int kg = 0; kg < 4; ++kg) {
+    float h[8];
+    const float4 ba = *reinterpret_cast<const float4*>(bias + kg * 8);
+    const float4 bb = *reinterpret_cast<const float4*>(bias + kg * 8 + 4);
+    h[0] = fmaxf(fmaf(v[kg * 8 + 0], kWUnscale, ba.x), 0.f); h[1] = fmaxf(fmaf(v[kg * 8 + 1], kWUnscale, ba.y), 0.f);
+    h[2] = fmaxf(fmaf(v[kg * 8 + 2], kWUnscale, ba.z), 0.f); h[3] = fmaxf(fmaf(v[kg * 8 + 3], kWUnscale, ba.w), 0.f);
+    h[4] = fmaxf(fmaf(v[kg * 8 + 4], kWUnscale, bb.x), 0.f); h[5] = fmaxf(fmaf(v[kg * 8 + 5], kWUnscale, bb.y), 0.f);
+    h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
+    tc::split8_f16_trunc(h, hi[kg], lo[kg]);
+  }
+  if (c > 0) tc_wait<2>(g.mL2, g.par);                                     // L2(c-1) complete -> A2 reusable
+#pragma unroll
+  for (int kg = 0; kg < 4; ++kg) {
+    *reinterpret_cast<uint4*>(g.pa2h + kg * 2048) = hi[kg];
+    *reinterpret_cast<uint4*>(g.pa2l + kg * 2048) = lo[kg];
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  tc::mbar_arrive(g.full);                                                 // A2(c) staged, D1[BUF] released
 }
 
-// One network for the group's current tile: x = this thread's input row.  On return the two accumulators
-// D2a (g.tD2) and D2b (g.tD2 + 32) are complete; their sum is W2^T relu(W1^T x + b1) * kWScale^... (see caller).
-__device__ __forceinline__ void tc_mlp_group(TcGroup& g, const TcNetDesc& nd, const float (&x)[16],
-                                             const float* __restrict__ sb1, int nchunk) {
-  // ---- stage the A operand of layer 1
+// compute-group side of one network: x = this thread's input row.  On return the accumulator D2 (2*NP columns:
+// [hi*hi + lo*hi | hi*lo]) is complete; (D2[:, :NP] + D2[:, NP:]) / kWScale = W2^T relu(W1^T x + b1).
+__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], const float* __restrict__ sb1, int nchunk) {
 #pragma unroll
   for (int kg = 0; kg < 2; ++kg) {
     float v[8];
@@ -118,54 +121,40 @@ __device__ __forceinline__ void tc_mlp_group(TcGroup& g, const TcNetDesc& nd, co
     for (int i = 0; i < 8; ++i) v[i] = x[kg * 8 + i];
     uint4 hi, lo;
     tc::split8_f16(v, hi, lo);
-    *reinterpret_cast<uint4*>(g.pa1h + kg * 2048 + g.gt * 16) = hi;
-    *reinterpret_cast<uint4*>(g.pa1l + kg * 2048 + g.gt * 16) = lo;
+    *reinterpret_cast<uint4*>(g.pa1h + kg * 2048) = hi;
+    *reinterpret_cast<uint4*>(g.pa1l + kg * 2048) = lo;
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
-  group_sync(g);
-  if (g.lane == 0 && (g.gw == 2 || g.gw == 3)) {     // L1(0) by warp 2, L1(1) by warp 3
-    tc::fence_after_sync();
-    const int c = g.gw - 2;
-    if (c < nchunk) tc_issue_l1(g, nd, c);
+  tc::mbar_arrive(g.full);
+  for (int c = 0; c < nchunk; c += 2) {
+    tc_chunk<0>(g, sb1, c);
+    if (c + 1 < nchunk) tc_chunk<1>(g, sb1, c + 1);
   }
-  __syncwarp();
-
-  for (int c = 0; c < nchunk; ++c) {
-    tc_wait(g.mD1 + (c & 1), g.par, c & 1);                               // L1(c) complete
-    tc::fence_after_sync();
-    float v[32];
-    tc::tmem_ld32(g.tD1 + g.lane_base + (c & 1) * 32, v);
-    uint4 hi[4], lo[4];
-#pragma unroll
-    for (int kg = 0; kg < 4; ++kg) {
-      float h[8];
-      const float4 ba = *reinterpret_cast<const float4*>(sb1 + c * kTcChunk + kg * 8);
-      const float4 bb = *reinterpret_cast<const float4*>(sb1 + c * kTcChunk + kg * 8 + 4);
-      h[0] = fmaxf(fmaf(v[kg * 8 + 0], kWUnscale, ba.x), 0.f); h[1] = fmaxf(fmaf(v[kg * 8 + 1], kWUnscale, ba.y), 0.f);
-      h[2] = fmaxf(fmaf(v[kg * 8 + 2], kWUnscale, ba.z), 0.f); h[3] = fmaxf(fmaf(v[kg * 8 + 3], kWUnscale, ba.w), 0.f);
-      h[4] = fmaxf(fmaf(v[kg * 8 + 4], kWUnscale, bb.x), 0.f); h[5] = fmaxf(fmaf(v[kg * 8 + 5], kWUnscale, bb.y), 0.f);
-      h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
-      tc::split8_f16(h, hi[kg], lo[kg]);
-    }
-    if (c > 0) { tc_wait(g.mL2, g.par, 2); tc_wait(g.mL2 + 1, g.par, 3); }   // L2(c-1) complete -> A2 reusable
-#pragma unroll
-    for (int kg = 0; kg < 4; ++kg) {
-      *reinterpret_cast<uint4*>(g.pa2h + kg * 2048 + g.gt * 16) = hi[kg];
-      *reinterpret_cast<uint4*>(g.pa2l + kg * 2048 + g.gt * 16) = lo[kg];
-    }
-    tc::fence_proxy_async();
-    tc::fence_before_sync();
-    group_sync(g);                                                         // A2(c) staged, D1[c&1] released
-    if (g.lane == 0 && g.gw < 3) {
-      tc::fence_after_sync();
-      if (g.gw < 2) tc_issue_l2(g, nd, c, g.gw);
-      else if (c + 2 < nchunk) tc_issue_l1(g, nd, c + 2);
-    }
-    __syncwarp();
-  }
-  tc_wait(g.mL2, g.par, 2); tc_wait(g.mL2 + 1, g.par, 3);                  // L2(last) complete
+  tc_wait<2>(g.mL2, g.par);                                                // L2(last) complete
   tc::fence_after_sync();
+}
+
+// MMA-warp side (one elected lane): L1(c) -> D1[c & 1]
+__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint32_t tD1, int c, uint64_t* mD1) {
+  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
+  const uint32_t d = tD1 + (c & 1) * 32;
+  const uint64_t bh = nd.w1h + (uint64_t)(c * (kTcChunk * 16 / 16)), bl = nd.w1l + (uint64_t)(c * (kTcChunk * 16 / 16));
+  tc::mma_bf16(d, a1h, bh, idesc1, false);
+  tc::mma_bf16(d, a1h, bl, idesc1, true);
+  tc::mma_bf16(d, a1l, bh, idesc1, true);
+  tc::mma_commit(mD1 + (c & 1));
+}
+// L2(c): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)  and  a_lo x w_hi (N = NP)
+__device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint64_t a2h, uint64_t a2l, uint32_t tD2, int c, uint64_t* mL2) {
+#pragma unroll
+  for (int ks = 0; ks < kTcChunk / 16; ++ks) {
+    const uint64_t b = nd.w2 + (uint64_t)((uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(2 * nd.NP));   // (2*NP*16 B per K-group) >> 4
+    const uint64_t ah = a2h + (uint64_t)(ks * (4096 / 16)), al = a2l + (uint64_t)(ks * (4096 / 16));
+    tc::mma_bf16(tD2, ah, b, nd.idesc2a, (c > 0) || (ks > 0));
+    tc::mma_bf16(tD2, al, b, nd.idesc2b, true);
+  }
+  tc::mma_commit(mL2);
 }
 
 template <int NPG>
@@ -175,7 +164,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const bool two_q = a.flags & PSVO_F_TWO_Q, poisson = a.flags & PSVO_F_POISSON;
   const bool t0 = a.t == 0;
   const TcPropSmem L = tc_prop_layout(H, NPG);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform (kept in a uniform register)
   const int nchunk = H / kTcChunk;
 
   float* sb1q = reinterpret_cast<float*>(sm + L.b1q);
@@ -184,18 +174,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][4]: mD1[0], mD1[1], mL2[0], mL2[1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][4]: full, mD1[0], mD1[1], mL2
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
   // ---- stage weights (fp16 hi/lo, UMMA B layout, pre-scaled), biases, constants
   if (!t0) {
     tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kWScale, sm + L.w1q_hi, sm + L.w1q_lo);
-    tc::stage_weight_f16x2(a.q1.W[1], H, Dx, H, 16, kWScale, sm + L.w2q_hi, sm + L.w2q_lo);
+    tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kWScale, sm + L.w2q);
     for (int i = tid; i < H; i += blockDim.x) sb1q[i] = __ldg(a.q1.b[0] + i);
     for (int i = tid; i < 16; i += blockDim.x) sb2q[i] = i < Dx ? __ldg(a.q1.b[1] + i) : 0.0f;
   }
   tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kWScale, sm + L.w1g_hi, sm + L.w1g_lo);
-  tc::stage_weight_f16x2(a.g.W[1], H, Dy, H, NPG, kWScale, sm + L.w2g_hi, sm + L.w2g_lo);
+  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kWScale, sm + L.w2g);
   for (int i = tid; i < H; i += blockDim.x) sb1g[i] = __ldg(a.g.b[0] + i);
   for (int i = tid; i < 32; i += blockDim.x) sb2g[i] = i < Dy ? __ldg(a.g.b[1] + i) : 0.0f;
   if (tid < 16) {
@@ -206,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
-  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, 1);
+  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -223,7 +213,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const int tiles_per_seq = (N + 127) / 128;
   const int work = a.B * tiles_per_seq;
 
-  {
+  TcNetDesc nq, ng;
+  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
+  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
+  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
+  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
+
+  if (warp >= kTcGroups * 4) {
+    // =================================== MMA-issuing warp of group (warp - 16) ===================================
+    const int grp = warp - kTcGroups * 4;
+    uint64_t* full = bars + 4 * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3;
+    const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
+    const uint64_t a2h = tc::make_desc(tc::smem_u32(sm + L.a2_hi[grp]), 2048, 128), a2l = tc::make_desc(tc::smem_u32(sm + L.a2_lo[grp]), 2048, 128);
+    const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
+    uint32_t phase = 0;
+    for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+      for (int net = t0 ? 1 : 0; net < 2; ++net) {
+        const TcNetDesc& nd = net ? ng : nq;
+        for (int s2 = 0; s2 <= nchunk; ++s2) {
+          tc::mbar_wait(full, phase); phase ^= 1;
+          tc::fence_after_sync();
+          if (lane == 0) {
+            if (s2 == 0) {
+              tc_issue_l1(nd, a1h, a1l, tD1, 0, mD1);
+              if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, tD1, 1, mD1);
+            } else {
+              tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
+              if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, tD1, s2 + 1, mD1);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
     const float* s1 = C; const float* sp = C + 16; const float* inv1 = C + 32; const float* inv2 = C + 48;
@@ -232,25 +257,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     const float neg_logN = -logf((float)N);
     (void)s1;
-    TcNetDesc nq, ng;
-    nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-    nq.w2h = tc::make_desc(tc::smem_u32(sm + L.w2q_hi), 16 * 16, 128); nq.w2l = tc::make_desc(tc::smem_u32(sm + L.w2q_lo), 16 * 16, 128);
-    nq.idesc2 = tc::make_idesc_f16(128, 16); nq.NP = 16;
-    ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-    ng.w2h = tc::make_desc(tc::smem_u32(sm + L.w2g_hi), NPG * 16, 128); ng.w2l = tc::make_desc(tc::smem_u32(sm + L.w2g_lo), NPG * 16, 128);
-    ng.idesc2 = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
     TcGroup g;
-    g.gt = tid & 127; g.gw = warp & 3; g.lane = lane; g.bar_id = 1 + grp;
-    g.mD1 = bars + 4 * grp; g.mL2 = bars + 4 * grp + 2; g.par = 0;
-    g.pa1h = sm + L.a1_hi[grp]; g.pa1l = sm + L.a1_lo[grp]; g.pa2h = sm + L.a2_hi[grp]; g.pa2l = sm + L.a2_lo[grp];
-    g.a1h = tc::make_desc(tc::smem_u32(g.pa1h), 2048, 128); g.a1l = tc::make_desc(tc::smem_u32(g.pa1l), 2048, 128);
-    g.a2h = tc::make_desc(tc::smem_u32(g.pa2h), 2048, 128); g.a2l = tc::make_desc(tc::smem_u32(g.pa2l), 2048, 128);
-    g.lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128; g.tD2 = tmem + grp * 128 + 64;
+    const int gt = tid & 127;
+    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
+    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
 
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const int b = wi / tiles_per_seq;
-      const int n = (wi - b * tiles_per_seq) * 128 + g.gt;
+      const int n = (wi - b * tiles_per_seq) * 128 + gt;
       const bool live = n < N;
       const size_t bt = (size_t)b * a.T + a.t;
       const size_t row = bt * N + (live ? n : 0);
@@ -285,10 +302,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         }
       }
       if (!t0) {
-        tc_mlp_group(g, nq, x, sb1q, nchunk);
+        tc_mlp_compute(g, x, sb1q, nchunk);
         float mb[16];
-        tc::tmem_ld16(g.tD2 + g.lane_base, mu1);
-        tc::tmem_ld16(g.tD2 + g.lane_base + 32, mb);
+        tc::tmem_ld16(g.tD2, mu1);
+        tc::tmem_ld16(g.tD2 + 16, mb);
 #pragma unroll
         for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d] + mb[d], kWUnscale, sb2q[d]);
       } else {
@@ -325,13 +342,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       }
 
       // ---- emission
-      tc_mlp_group(g, ng, x, sb1g, nchunk);
+      tc_mlp_compute(g, x, sb1g, nchunk);
       float gsum = 0.f;
 #pragma unroll
       for (int c = 0; c < NPG; c += 16) {
         float mug[16], mgb[16];
-        tc::tmem_ld16(g.tD2 + g.lane_base + c, mug);
-        tc::tmem_ld16(g.tD2 + g.lane_base + 32 + c, mgb);
+        tc::tmem_ld16(g.tD2 + c, mug);
+        tc::tmem_ld16(g.tD2 + NPG + c, mgb);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int d = c + i;

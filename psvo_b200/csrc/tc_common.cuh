@@ -164,6 +164,24 @@ __device__ __forceinline__ void split8_f16(const float (&x)[8], uint4& hi, uint4
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Truncating fp16 split for the hot epilogue: hi = x with the mantissa cut to fp16's 10 stored bits (one LOP3,
+// exactly representable in fp16 for |x| in fp16's normal range), lo = fp16(x - hi) (exact subtraction, one
+// rounding).  Residual <= 2^-21 |x|; no fp16 -> fp32 conversion is needed to form lo.
+__device__ __forceinline__ void split8_f16_trunc(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float h0 = __uint_as_float(__float_as_uint(x[2 * i]) & 0xFFFFE000u);
+    const float h1 = __uint_as_float(__float_as_uint(x[2 * i + 1]) & 0xFFFFE000u);
+    const __half2 hh = __floats2half2_rn(h0, h1);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // fp16 weight staging: W * scale split as hi + lo (scale is a power of two, undone in the epilogue)
 __device__ __forceinline__ void stage_weight_f16x2(const float* __restrict__ W, int n_in, int n_out, int KP, int NP, float scale,
                                                    unsigned char* hi, unsigned char* lo) {
@@ -175,6 +193,22 @@ __device__ __forceinline__ void stage_weight_f16x2(const float* __restrict__ W, 
     const size_t off = (size_t)(k >> 3) * (NP * 16) + (size_t)n * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(hi + off) = h;
     *reinterpret_cast<__half*>(lo + off) = l;
+  }
+}
+
+// same, hi and lo stacked along N inside one operand: per K-group NP "hi" rows followed by NP "lo" rows, so that
+// one MMA with N = 2*NP evaluates a*w_hi and a*w_lo side by side, and an MMA with N = NP on the same descriptor
+// (same LBO) sees only the hi rows.
+__device__ __forceinline__ void stage_weight_f16x2_stacked(const float* __restrict__ W, int n_in, int n_out, int KP, int NP,
+                                                           float scale, unsigned char* dst) {
+  for (int i = threadIdx.x; i < NP * KP; i += blockDim.x) {
+    const int n = i % NP, k = i / NP;
+    const float w = (n < n_out && k < n_in) ? __ldg(W + (size_t)k * n_out + n) * scale : 0.0f;
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const size_t off = (size_t)(k >> 3) * (2 * NP * 16) + (size_t)n * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = h;
+    *reinterpret_cast<__half*>(dst + off + NP * 16) = l;
   }
 }
 
