@@ -86,7 +86,7 @@ int check_dims(const psvo_dims* d) {
   return 0;
 }
 
-struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; size_t bytes; };
+struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; unsigned char* tc_image; size_t bytes; };
 
 FwdWs carve_fwd(const psvo_dims* d, void* ws) {
   FwdWs w;
@@ -98,6 +98,7 @@ FwdWs carve_fwd(const psvo_dims* d, void* ws) {
   w.mu0 = take((size_t)d->B * d->Dx);
   w.muf0 = take((size_t)d->B * d->Dx);
   w.logWbar = take((size_t)d->B * d->N);
+  w.tc_image = reinterpret_cast<unsigned char*>(take(32 * 1024));      // 128 KB: fp16 weight image of the tensor-core path
   w.bytes = off;
   return w;
 }
@@ -199,8 +200,13 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
   pa.eps = eps; pa.logWbar = resample ? nullptr : w.logWbar;
   pa.X_anc = X_anc; pa.Xs = Xs; pa.log_Ws = log_Ws;
   pa.seed = seed; pa.N = d->N; pa.B = d->B; pa.T = d->T; pa.Dx = d->Dx; pa.Dy = d->Dy; pa.t = 0;
-  pa.seq_offset = d->seq_offset; pa.scratch_half = 0; pa.flags = d->flags;
+  pa.seq_offset = d->seq_offset; pa.scratch_half = 0; pa.flags = d->flags; pa.tc_image = nullptr;
   const PropPlan plan = plan_propagate(pa);
+  if (tc_propagate_supported(pa)) {
+    PSVO_REQUIRE(tc_image_bytes(pa) <= 128 * 1024, "tensor-core weight image too large");
+    if (int e = launch_tc_stage_image(pa, w.tc_image, st)) return e;
+    pa.tc_image = w.tc_image;
+  }
 
   ResampleArgs ra;
   ra.log_Ws = log_Ws; ra.Xs = Xs; ra.u = u; ra.forced_anc = forced_anc; ra.X_anc = X_anc; ra.anc = anc;

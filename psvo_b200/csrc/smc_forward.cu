@@ -277,7 +277,7 @@ PropPlan plan_propagate(const PropArgs& a) {
 }
 
 int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
-  if (tc_propagate_supported(a)) return launch_propagate_tc(a, st);
+  if (a.tc_image != nullptr && tc_propagate_supported(a)) return launch_propagate_tc(a, st);
   a.scratch_half = pl.scratch_half;
   const int DXP = pad_dx(a.Dx), DYP = pad_dy(a.Dy);
   PSVO_REQUIRE(pl.smem <= 227 * 1024, "MLP weights (%zu B) exceed one SM's shared memory", pl.smem);

@@ -27,6 +27,7 @@ struct PropArgs {
   const float* X_anc;      // (B,T,N,Dx) read at t-1
   float* Xs;               // (B,T,N,Dx) written at t
   float* log_Ws;           // (B,T,N)    written at t
+  const unsigned char* tc_image;   // staged fp16 weight image for the tensor-core path (launch_tc_stage_image) or NULL
   unsigned long long seed;
   int N, B, T, Dx, Dy, t, seq_offset, scratch_half;
   unsigned flags;
@@ -59,6 +60,8 @@ int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g
 
 // tensor-core (tcgen05) propagate step (smc_propagate_tc.cu)
 bool tc_propagate_supported(const PropArgs& a);
+size_t tc_image_bytes(const PropArgs& a);
+int launch_tc_stage_image(const PropArgs& a, unsigned char* image, cudaStream_t st);
 int launch_propagate_tc(const PropArgs& a, cudaStream_t st);
 
 // tensor-core (tcgen05) one-hidden-layer MLP over particle rows (tc_mlp.cu)

@@ -157,6 +157,25 @@ __device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint64_t a2h, u
   tc::mma_commit(mL2);
 }
 
+// fp16 weight image (layout = the head of TcPropSmem), written once per forward pass
+template <int NPG>
+__global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigned char* __restrict__ img) {
+  const int Dx = a.Dx, Dy = a.Dy, H = a.g.width[0];
+  const TcPropSmem L = tc_prop_layout(H, NPG);
+  const int tid = threadIdx.x;
+  for (uint32_t i = tid; i < L.consts / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
+  __syncthreads();
+  tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kWScale, img + L.w1q_hi, img + L.w1q_lo);
+  tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kWScale, img + L.w2q);
+  tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kWScale, img + L.w1g_hi, img + L.w1g_lo);
+  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kWScale, img + L.w2g);
+  float* b1q = reinterpret_cast<float*>(img + L.b1q); float* b2q = reinterpret_cast<float*>(img + L.b2q);
+  float* b1g = reinterpret_cast<float*>(img + L.b1g); float* b2g = reinterpret_cast<float*>(img + L.b2g);
+  for (int i = tid; i < H; i += blockDim.x) { b1q[i] = __ldg(a.q1.b[0] + i); b1g[i] = __ldg(a.g.b[0] + i); }
+  for (int i = tid; i < 16; i += blockDim.x) b2q[i] = i < Dx ? __ldg(a.q1.b[1] + i) : 0.0f;
+  for (int i = tid; i < 32; i += blockDim.x) b2g[i] = i < Dy ? __ldg(a.g.b[1] + i) : 0.0f;
+}
+
 template <int NPG>
 __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -177,17 +196,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][4]: full, mD1[0], mD1[1], mL2
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
-  // ---- stage weights (fp16 hi/lo, UMMA B layout, pre-scaled), biases, constants
-  if (!t0) {
-    tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kWScale, sm + L.w1q_hi, sm + L.w1q_lo);
-    tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kWScale, sm + L.w2q);
-    for (int i = tid; i < H; i += blockDim.x) sb1q[i] = __ldg(a.q1.b[0] + i);
-    for (int i = tid; i < 16; i += blockDim.x) sb2q[i] = i < Dx ? __ldg(a.q1.b[1] + i) : 0.0f;
+  // ---- weights (fp16 hi/lo, UMMA B layout, pre-scaled) and biases: one coalesced copy of the image that
+  //      tc_stage_image_kernel prepared once for this forward pass
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    const int n16 = (int)(L.consts / 16);
+#pragma unroll 4
+    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kWScale, sm + L.w1g_hi, sm + L.w1g_lo);
-  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kWScale, sm + L.w2g);
-  for (int i = tid; i < H; i += blockDim.x) sb1g[i] = __ldg(a.g.b[0] + i);
-  for (int i = tid; i < 32; i += blockDim.x) sb2g[i] = i < Dy ? __ldg(a.g.b[1] + i) : 0.0f;
   if (tid < 16) {
     const int d = tid;
     const float s1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d], s2 = a.sig[SIG_Q2 * 32 + d];
@@ -386,7 +403,17 @@ bool tc_propagate_supported(const PropArgs& a) {
   return true;
 }
 
+size_t tc_image_bytes(const PropArgs& a) { return tc_prop_layout(a.g.width[0], 32).consts; }
+
+int launch_tc_stage_image(const PropArgs& a, unsigned char* image, cudaStream_t st) {
+  ProfScope ps_(PK_ROWS, st);
+  tc_stage_image_kernel<32><<<1, 512, 0, st>>>(a, image);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
+  PSVO_REQUIRE(a.tc_image != nullptr, "tensor-core propagate: weight image missing");
   const int H = a.g.width[0];
   const int NPG = 32;      // one instantiation: the emission head is padded to 32 outputs
   const TcPropSmem L = tc_prop_layout(H, NPG);

@@ -3,7 +3,8 @@
 // Reference: MLP_transformation.transform (src/transformation/MLP.py:48-54) for rows that are particles:
 // d_in <= 16, one hidden layer of width H (multiple of 16, <= 256), d_out <= 32 -- the shape of q1 / f / g /
 // q1_inv at BASELINE config 5.  Used by psvo_mlp_forward when the shape fits and the row count is large, and
-// by the FFBSi step's per-particle nets.  Arithmetic: bf16x3 split products, fp32 accumulation (tc_common.cuh).
+// by the FFBSi step's per-particle nets.  Arithmetic: fp16x3 split products with 2^8 pre-scaled weights, fp32
+// accumulation (tc_common.cuh, smc_propagate_tc.cu).
 //
 // One CTA = 128 threads = one 128-row tile at a time (TMEM lane == row == thread):
 //   threads : load the row, split to bf16 hi/lo, store as the A operand                        (CUDA cores)
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + L.bar);
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
-  tc::stage_weight_bf16x2(net.W[0], din, H, 16, H, sm + L.w1_hi, sm + L.w1_lo);
-  tc::stage_weight_bf16x2(net.W[1], H, dout, H, NP, sm + L.w2_hi, sm + L.w2_lo);
+  tc::stage_weight_f16x2(net.W[0], din, H, 16, H, 256.0f, sm + L.w1_hi, sm + L.w1_lo);
+  tc::stage_weight_f16x2(net.W[1], H, dout, H, NP, 256.0f, sm + L.w2_hi, sm + L.w2_lo);
   for (int i = tid; i < H; i += blockDim.x) sb1[i] = __ldg(net.b[0] + i);
   for (int i = tid; i < NP; i += blockDim.x) sb2[i] = i < dout ? __ldg(net.b[1] + i) : 0.0f;
   if (tid == 0) tc::mbar_init(mbar, 1);
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
   const uint32_t tmem = *slot;
   const uint32_t tD1 = tmem, tD2 = tmem + 256;                       // column offsets
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const uint32_t idesc1 = tc::make_idesc_bf16(128, H), idesc2 = tc::make_idesc_bf16(128, NP);
+  const uint32_t idesc1 = tc::make_idesc_f16(128, H), idesc2 = tc::make_idesc_f16(128, NP);
   const uint32_t a1h = tc::smem_u32(sm + L.a1_hi), a1l = tc::smem_u32(sm + L.a1_lo);
   const uint32_t a2h = tc::smem_u32(sm + L.a2_hi), a2l = tc::smem_u32(sm + L.a2_lo);
   const uint32_t w1h = tc::smem_u32(sm + L.w1_hi), w1l = tc::smem_u32(sm + L.w1_lo);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = x[kg * 8 + i];
         uint4 hi, lo;
-        tc::split8(v, hi, lo);
+        tc::split8_f16(v, hi, lo);
         *reinterpret_cast<uint4*>(sm + L.a1_hi + kg * 2048 + tid * 16) = hi;
         *reinterpret_cast<uint4*>(sm + L.a1_lo + kg * 2048 + tid * 16) = lo;
       }
@@ -113,9 +114,9 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
       for (int g = 0; g < 2; ++g) {
         float h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = fmaxf(v[g * 8 + i] + sb1[c + g * 8 + i], 0.0f);
+        for (int i = 0; i < 8; ++i) h[i] = fmaxf(fmaf(v[g * 8 + i], 1.0f / 256.0f, sb1[c + g * 8 + i]), 0.0f);
         uint4 hi, lo;
-        tc::split8(h, hi, lo);
+        tc::split8_f16(h, hi, lo);
         const int kg = (c >> 3) + g;
         *reinterpret_cast<uint4*>(sm + L.a2_hi + kg * 2048 + tid * 16) = hi;
         *reinterpret_cast<uint4*>(sm + L.a2_lo + kg * 2048 + tid * 16) = lo;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
       tc::tmem_ld16(tD2 + lane_base + c, v);
       if (live) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (c + i < dout) out[r * dout + c + i] = v[i] + sb2[c + i];
+        for (int i = 0; i < 16; ++i) if (c + i < dout) out[r * dout + c + i] = fmaf(v[i], 1.0f / 256.0f, sb2[c + i]);
       }
     }
     tc::fence_before_sync();
