@@ -35,10 +35,16 @@ class SVO:
         Extra keyword arguments (parity / reproducibility): eps (B,T,N,Dx), uniforms (B,T,N),
         forced_ancestors (B,T,N), seed (Philox key; default: FLAGS.seed advanced per call).
         Returns (log_ZSMC scalar, differentiable; {"Xs": (B,T,N,Dx)})."""
+        logZ_b, log = self._filter_objective(obs, eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors,
+                                             seed=seed, out=out)
+        return logZ_b.mean(), log                                             # SVO.py:308-309
+
+    def _filter_objective(self, obs, eps=None, uniforms=None, forced_ancestors=None, seed=None, out=None):
+        """Per-sequence objective logZ_b (B,) (log_ZSMC = its batch mean) and the log dict; the sequence-sharded
+        multi-GPU wrapper (psvo_b200.distributed) reduces logZ_b over ranks itself."""
         logZ_b, aux = self._filter(obs, eps, uniforms, forced_ancestors, seed, out)
-        log_ZSMC = logZ_b.mean()                                              # SVO.py:308-309
         self.last = aux
-        return log_ZSMC, {"Xs": aux["X_anc"]}                                 # SVO.py:51-56
+        return logZ_b, {"Xs": aux["X_anc"]}                                   # SVO.py:51-56
 
     def SMC(self, hidden, obs, q_cov=1.0, **kw):
         """Reference layout: Xs, X_ancestors (T,N,B,Dx), log_Ws (T,N,B) (permuted views, no copy)."""

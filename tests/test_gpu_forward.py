@@ -210,6 +210,28 @@ def test_philox_mode_equals_materialised_draws():
     assert torch.equal(c["log_Ws"][0], a["log_Ws"][1]) and torch.equal(c["anc"][0], a["anc"][1])
 
 
+def test_sharded_equals_whole_batch():
+    """sequences [first, first+count) run with seq_offset=first reproduce the whole-batch run bit for
+    bit (in-kernel Philox is keyed by the global sequence index), so logZ_b shards concatenate."""
+    from psvo_b200.distributed import shard_bounds
+    name, Dx, Dy, Dobs, Dx0, hidden, N, B, T, F = CONFIGS[0]
+    B = 5
+    P, obs, pre_obs, pre_x0, _, _ = make_case(Dx, Dy, Dobs, Dx0, hidden, N, B, T, F)
+    f = Fn()
+    Pd = to_dev(P)
+    whole = f.smc_forward_raw(Pd, flags_of(F), obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N, seed=77)
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            first, count = shard_bounds(B, rank, world)
+            sl = slice(first, first + count)
+            r = f.smc_forward_raw(Pd, flags_of(F), obs[sl].to(DEV), pre_obs[sl].to(DEV), pre_x0[sl].to(DEV), N, seed=77,
+                                  seq_offset=first)
+            parts.append(r)
+        for k in ("Xs", "X_anc", "anc", "log_Ws", "logZ_b"):
+            assert torch.equal(torch.cat([p[k] for p in parts], 0), whole[k]), (world, k)
+
+
 def test_kalman_known_answer_on_gpu():
     """config-3 analogue: linear-Gaussian SSM, AESMC bootstrap filter vs the analytic Kalman log-likelihood"""
     from test_oracle import _lds
