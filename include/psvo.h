@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSVO_VERSION 100          /* 0.1.0 */
+#define PSVO_VERSION 200          /* 0.2.0 */
 #define PSVO_MAX_HIDDEN 4         /* hidden layers per MLP_transformation */
 #define PSVO_MAX_DX 16            /* latent dimension the fused kernels are instantiated for */
 #define PSVO_MAX_DY 32            /* observation dimension the fused kernels are instantiated for */
@@ -128,13 +128,15 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p,
  * Replaces what optimizer.minimize(-log_ZSMC) derives through SVO.SMC (src/trainer.py:115-118): path-wise
  * gradients through the reparameterised samples and the ancestor gather; none into the resampling logits.
  * Consumes the forward outputs (recomputes MLP activations).  g_logZ_b (B) = d loss / d logZ_b.
- * g_pre_obs (B,T,Dobs) and g_pre_x0 (B,Dx0) are overwritten; grads are accumulated. */
+ * g_Xs (B,T,N,Dx) / g_log_Ws (B,T,N) or NULL: additional incoming gradients w.r.t. the filter's particles and log
+ * weights -- what psvo_ffbsi_backward returns, because the smoothing objectives read X_prevs and log_Ws
+ * (src/SMC/PSVO.py:39-40).  g_pre_obs (B,T,Dobs) and g_pre_x0 (B,Dx0) are overwritten; grads are accumulated. */
 PSVO_API size_t psvo_smc_backward_workspace_bytes(const psvo_dims* d, const psvo_params* p);
 PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p,
                       const float* obs, const float* pre_obs, const float* pre_x0,
                       const float* eps, uint64_t seed,
                       const float* Xs, const float* X_anc, const int32_t* anc, const float* log_Ws,
-                      const float* lse, const float* g_logZ_b,
+                      const float* lse, const float* g_logZ_b, const float* g_Xs, const float* g_log_Ws,
                       psvo_grads* grads, float* g_pre_obs, float* g_pre_x0,
                       void* ws, size_t ws_bytes, psvo_stream_t stream);
 
@@ -158,6 +160,27 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p,
                        float* bw_Xs, int32_t* pick, float* f_lp, float* g_lp, float* Omega_or_bw_log_W,
                        float* bw_X_anc, int32_t* anc2, float* omega_all, float* logZ_b,
                        void* ws, size_t ws_bytes, psvo_stream_t stream);
+
+/* ---- reverse mode of the backward simulation --------------------------------------------------------------
+ * Replaces what optimizer.minimize(-log_ZSMC) (src/trainer.py:115-118) derives through
+ * PSVO.backward_simulation_w_proposal + compute_log_ZSMC (src/SMC/PSVO.py:52-203) / the PSVOwR variants
+ * (src/SMC/PSVOwR.py:52-198): path-wise gradients through the reparameterised candidates, the gather of the picked
+ * candidate (and PSVOwR's second gather), the MLP log densities, the pairwise predictive term and the normalisation
+ * over the M candidates; none into the 1-of-M pick / resampling logits.  Candidates are recomputed from eps_bw or
+ * Philox(seed) and the stored picks.  Inputs after `seed` are outputs of psvo_ffbsi_forward.
+ * Outputs: parameter gradients ACCUMULATED into grads (f-gradients into q1 under PSVO_F_BOOTSTRAP);
+ *   g_bs_feat (B,T,Dfeat) or NULL and g_pre_x0 (B,Dx0) or NULL are overwritten;
+ *   g_Xs (B,T,N,Dx) and g_log_Ws (B,T,N) are overwritten: feed them to psvo_smc_backward (with g_logZ_b = 0). */
+PSVO_API size_t psvo_ffbsi_backward_workspace_bytes(const psvo_dims* d, const psvo_params* p);
+PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p,
+                        const float* obs, const float* bs_feat, const float* pre_x0,
+                        const float* Xs, const float* log_Ws, const float* lse,
+                        const float* eps_bw, uint64_t seed,
+                        const float* bw_Xs, const int32_t* pick, const float* f_lp, const float* g_lp,
+                        const float* Omega_or_bw_log_W, const float* bw_X_anc, const int32_t* anc2,
+                        const float* g_logZ_b,
+                        psvo_grads* grads, float* g_bs_feat, float* g_pre_x0, float* g_Xs, float* g_log_Ws,
+                        void* ws, size_t ws_bytes, psvo_stream_t stream);
 
 /* ---- stand-alone operators (API parity + unit tests) ----------------------------------------------------
  * psvo_resample       SVO.get_resample_idx (SVO.py:266-300): logits (rows,K), u (rows,n) -> idx (rows,n)

@@ -2,23 +2,13 @@
 
 Interface of src/SMC/PSVO.py: PSVO(model, FLAGS), get_log_ZSMC(obs, hidden) -> (log_ZSMC, {"Xs": bw_Xs (B,T,N,Dx)}),
 backward_simulation_w_proposal(Xs, log_Ws, obs), compute_log_ZSMC(f, g, Omega), BS_preprocess_obs(obs).
-Round-1 status: the forward value runs on the GPU kernels (psvo_ffbsi_forward); its reverse mode
-(psvo_ffbsi_backward) is not built yet, so the returned log_ZSMC raises if back-propagated."""
+The objective is differentiable end to end: psvo_ffbsi_backward chained into psvo_smc_backward (ops.SmoothingFn),
+with the bi-LSTM features and the MLP parameters receiving gradients exactly where TF autodiff would put them."""
 import torch
 
 from .. import functional as Fn
+from .. import ops
 from .SVO import SVO
-
-
-class _NoGradYet(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, value, *leaves):
-        return value.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError("reverse mode of the FFBSi backward simulation (psvo_ffbsi_backward) is not built yet; "
-                                  "SVO / AESMC / IWAE objectives are differentiable")
 
 
 class PSVO(SVO):
@@ -38,16 +28,37 @@ class PSVO(SVO):
 
     def get_log_ZSMC(self, obs, hidden=None, eps=None, uniforms=None, forced_ancestors=None, seed=None,
                      eps_bw=None, uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None):
-        with torch.no_grad():
-            _, aux = self._filter(obs, eps, uniforms, forced_ancestors, seed, out)        # PSVO.py:39
-            used_seed = self._last_seed
-            bs = self.backward_simulation_w_proposal(aux["Xs"], aux["log_Ws"], obs, lse=aux["lse"], eps_bw=eps_bw,
-                                                     uniforms_pick=uniforms_pick, uniforms_res=uniforms_res,
-                                                     forced_pick=forced_pick, forced_anc2=forced_anc2, seed=used_seed)
-        self.last = dict(filter=aux, bsim=bs)
-        log_ZSMC = _NoGradYet.apply(bs["logZ_b"].mean(), *[p for p in self.model.parameters()][:1])
-        Xs = bs["bw_X_anc"] if self.with_resampling else bs["bw_Xs"]                      # PSVO.py:43, PSVOwR.py:43
-        return log_ZSMC, {"Xs": Xs}
+        logZ_b, log = self._filter_objective(obs, eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors, seed=seed,
+                                             eps_bw=eps_bw, uniforms_pick=uniforms_pick, uniforms_res=uniforms_res,
+                                             forced_pick=forced_pick, forced_anc2=forced_anc2, out=out)
+        return logZ_b.mean(), log                                                         # PSVO.py:65
+
+    def _filter_objective(self, obs, eps=None, uniforms=None, forced_ancestors=None, seed=None, eps_bw=None,
+                          uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None):
+        """Per-sequence smoothing objective logZ_b (B,) and the log dict (PSVO.py:39-48)."""
+        if obs.dim() != 3:
+            raise ValueError("obs must be (batch_size, time, Dy)")
+        m = self.model
+        self.batch_size, self.time, self.Dx = obs.shape[0], obs.shape[1], m.Dx
+        pre_X0, pre_obs = self.preprocess_obs(obs)                                        # smooth_obs=False: raw obs
+        self.preprocessed_X0, self.preprocessed_obs = pre_X0, pre_obs
+        self._build_nets(pre_X0.shape[-1], pre_obs.shape[-1], obs.device)
+        _, feats = self.BS_preprocess_obs(obs)                                            # PSVO.py:80
+        feats = feats.contiguous()
+        m.BSim_q_init_tran.build(feats.shape[-1], obs.device)
+        m.BSim_q2_tran.build(feats.shape[-1], obs.device)
+        m.to(obs.device)
+        if seed is None:
+            seed = (self.seed << 20) + self._calls
+            self._calls += 1
+        self._last_seed = seed
+        flags = Fn.flag_bits(m.use_bootstrap, m.use_2_q, True, m.poisson_emission, self.with_resampling)
+        logZ_b, Xout, last = ops.smoothing_objective(
+            m.dist_params(), flags, obs, pre_obs, pre_X0, feats, self.n_particles, self.n_particles_for_BSim_proposal,
+            eps=eps, u=uniforms, forced_anc=forced_ancestors, eps_bw=eps_bw, u_pick=uniforms_pick, u_res=uniforms_res,
+            forced_pick=forced_pick, forced_anc2=forced_anc2, seed=seed, seq_offset=self.seq_offset, out=out)
+        self.last = last
+        return logZ_b, {"Xs": Xout}                                                       # PSVO.py:43, PSVOwR.py:43
 
     def _filter(self, obs, eps, u, forced, seed, out):
         if seed is None:

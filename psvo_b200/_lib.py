@@ -52,8 +52,12 @@ SIGNATURES = {
     "psvo_smc_forward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psvo_smc_backward_workspace_bytes": (_sz, [_dp, _pp]),
-    "psvo_smc_backward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp,
+    "psvo_smc_backward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     C.POINTER(psvo_grads), _vp, _vp, _vp, _sz, _vp]),
+    "psvo_ffbsi_backward_workspace_bytes": (_sz, [_dp, _pp]),
+    "psvo_ffbsi_backward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      C.POINTER(psvo_grads), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psvo_ffbsi_workspace_bytes": (_sz, [_dp, _pp]),
     "psvo_ffbsi_forward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

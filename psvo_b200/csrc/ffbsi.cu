@@ -75,6 +75,15 @@ static int launch_particle_mlp(const psvo_mlp& net, const float* in, long long s
   return 0;
 }
 
+// out (B,N,Dx) = MLP(in[b*seq_stride + n*Dx ...]) for a Dx -> Dx network (shared with ffbsi_backward.cu)
+int launch_particle_mlp_dx(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, int Dx, float* out,
+                           cudaStream_t st) {
+  const int DXP = pad_dx(Dx);
+  return DXP == 4 ? launch_particle_mlp<4>(net, in, seq_stride, B, N, Dx, out, st)
+                  : (DXP == 8 ? launch_particle_mlp<8>(net, in, seq_stride, B, N, Dx, out, st)
+                              : launch_particle_mlp<16>(net, in, seq_stride, B, N, Dx, out, st));
+}
+
 struct FfbsiArgs {
   psvo_mlp f, g;
   const float* sig;

@@ -31,6 +31,8 @@ struct BwdArgs {
   const float* obs; const float* mu2_all; const float* mu0; const float* muf0;
   const float* Xs; const float* X_anc; const int* anc; const float* log_Ws; const float* lse;
   const float* g_logZ_b;
+  const float* g_Xs;      // (B,T,N,Dx) incoming d/dXs (FFBSi reverse mode) or NULL
+  const float* g_log_Ws;  // (B,T,N)    incoming d/dlog_Ws or NULL
   float* gXg;        // (B,N,Dx) emission contribution to d/dX_t         (written by bwd_emission)
   const float* gXin; // (B,N,Dx) children contribution to d/dX_t         (scattered by step t+1)
   float* gXout;      // (B,N,Dx) d/dX_{t-1} accumulator (zeroed before the launch)
@@ -47,7 +49,9 @@ __device__ __forceinline__ float particle_weight_grad(const BwdArgs& a, int b, i
   if (!live) return 0.0f;
   const bool resample = a.flags & PSVO_F_RESAMPLE;
   const size_t bt = (size_t)b * a.T + (resample ? a.t : a.T - 1);
-  return expf(a.log_Ws[bt * a.N + n] - a.lse[bt]) * a.g_logZ_b[b];
+  float g = expf(a.log_Ws[bt * a.N + n] - a.lse[bt]) * a.g_logZ_b[b];
+  if (a.g_log_Ws != nullptr) g += a.g_log_Ws[((size_t)b * a.T + a.t) * a.N + n];     // resampling mode only (checked by the ABI)
+  return g;
 }
 
 template <int DXP, int DYP>
@@ -206,7 +210,8 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
         const float m = two_q ? sp[d] * A : mu1[0][d];
         const float e = (X - m) / sp[d];
         const float zf = (X - muf[0][d]) / sf[d];
-        const float gX = a.gXin[bn * Dx + d] + a.gXg[bn * Dx + d] - gl * zf / sf[d];
+        float gX = a.gXin[bn * Dx + d] + a.gXg[bn * Dx + d] - gl * zf / sf[d];
+        if (a.g_Xs != nullptr) gX += a.g_Xs[(bt * N + n) * Dx + d];
         // X = m + sp*e ; -q_lp contributes +gl/sp to d/dsp, nothing to d/dm
         st_sp[d] += gX * e + gl / sp[d] + (two_q ? gX * A : 0.0f);
         st_sf[d] += gl * (zf * zf - 1.0f) / sf[d];
@@ -400,7 +405,7 @@ PSVO_API size_t psvo_smc_backward_workspace_bytes(const psvo_dims* d, const psvo
 PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const float* obs, const float* pre_obs,
                                const float* pre_x0, const float* eps, uint64_t seed, const float* Xs, const float* X_anc,
                                const int32_t* anc, const float* log_Ws, const float* lse, const float* g_logZ_b,
-                               psvo_grads* grads, float* g_pre_obs, float* g_pre_x0, void* ws, size_t ws_bytes,
+                               const float* g_Xs, const float* g_log_Ws, psvo_grads* grads, float* g_pre_obs, float* g_pre_x0, void* ws, size_t ws_bytes,
                                psvo_stream_t stream) {
   (void)eps; (void)seed;     // the noise is recovered as (X - m)/s from the stored particles
   if (int e = check_dims(d)) return e;
@@ -409,6 +414,8 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   const bool two_q = d->flags & PSVO_F_TWO_Q, boot = d->flags & PSVO_F_BOOTSTRAP;
   const bool f_is_d1 = boot && two_q, sep_f = !boot;
   PSVO_REQUIRE(!two_q || pre_obs, "psvo_smc_backward: pre_obs is null but use_2_q is set");
+  PSVO_REQUIRE(g_log_Ws == nullptr || (d->flags & PSVO_F_RESAMPLE),
+               "psvo_smc_backward: an incoming g_log_Ws is only supported with resampling (PSVO / PSVOwR always resample)");
   const psvo_dist& fd = boot ? p->q1 : p->f;
   PSVO_REQUIRE(p->q1.net.n_hidden <= 1 && p->g.net.n_hidden <= 1 && fd.net.n_hidden <= 1,
                "psvo_smc_backward: per-particle networks (q1, f, g) with more than one hidden layer are not supported by the reverse-mode kernels yet");
@@ -434,6 +441,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   a.gq1 = grads->q1.net; a.gf = boot ? grads->q1.net : grads->f.net; a.gg = grads->g.net;
   a.sig = w.sig; a.obs = obs; a.mu2_all = w.mu2_all; a.mu0 = w.mu0; a.muf0 = w.muf0;
   a.Xs = Xs; a.X_anc = X_anc; a.anc = anc; a.log_Ws = log_Ws; a.lse = lse; a.g_logZ_b = g_logZ_b;
+  a.g_Xs = g_Xs; a.g_log_Ws = g_log_Ws;
   a.gXg = w.gXg; a.gmu2_all = w.gmu2_all; a.gmu0 = w.gmu0; a.gmuf0 = w.gmuf0; a.stats = w.stats;
   a.N = N; a.B = B; a.T = T; a.Dx = Dx; a.Dy = d->Dy; a.flags = d->flags;
 

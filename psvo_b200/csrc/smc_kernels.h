@@ -58,6 +58,10 @@ int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, f
 int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g_mu, int64_t rows,
                              float* g_x, const psvo_mlp_grad* grads, cudaStream_t st);
 
+// per-particle Dx -> Dx MLP over (B,N) rows read with a per-sequence stride (ffbsi.cu)
+int launch_particle_mlp_dx(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, int Dx, float* out,
+                           cudaStream_t st);
+
 // tensor-core (tcgen05) propagate step (smc_propagate_tc.cu)
 bool tc_propagate_supported(const PropArgs& a);
 size_t tc_image_bytes(const PropArgs& a);

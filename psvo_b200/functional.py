@@ -153,9 +153,33 @@ def smc_forward_raw(P: dict, flags: int, obs, pre_obs, pre_x0, N, eps=None, u=No
     return dict(Xs=Xs, X_anc=X_anc, anc=anc, log_Ws=log_Ws, lse=lse, logZ_b=logZ_b, ws=ws)
 
 
+def alloc_grads(P: dict, dev, into=None):
+    """zero-filled gradient buffers with the topology of P -> (psvo_grads struct, {name: {W, b, sigma_con}}).
+    `into`: an existing dict of buffers to accumulate into (the C ABI adds)."""
+    gs = L.psvo_grads()
+    grads = {} if into is None else into
+    for name in DIST_NAMES:
+        dp = P.get(name)
+        if dp is None:
+            continue
+        if name not in grads:
+            grads[name] = dict(W=[torch.zeros(w.shape, device=dev, dtype=torch.float32) for w in dp.Ws],
+                               b=[torch.zeros(b.shape, device=dev, dtype=torch.float32) for b in dp.bs],
+                               sigma_con=None if dp.sigma_con is None else
+                               torch.zeros(dp.sigma_con.shape, device=dev, dtype=torch.float32))
+        g = grads[name]
+        gd = getattr(gs, name)
+        for k in range(len(g["W"])):
+            gd.net.W[k], gd.net.b[k] = g["W"][k].data_ptr(), g["b"][k].data_ptr()
+        if g["sigma_con"] is not None:
+            gd.sigma_con = g["sigma_con"].data_ptr()
+    return gs, grads
+
+
 def smc_backward_raw(P: dict, flags: int, obs, pre_obs, pre_x0, N, eps, seed, seq_offset,
-                     Xs, X_anc, anc, log_Ws, lse, g_logZ_b):
-    """psvo_smc_backward.  Returns dict(grads={name: {W: [...], b: [...], sigma_con}}, g_pre_obs, g_pre_x0)."""
+                     Xs, X_anc, anc, log_Ws, lse, g_logZ_b, g_Xs=None, g_log_Ws=None, grads_into=None):
+    """psvo_smc_backward.  Returns dict(grads={name: {W: [...], b: [...], sigma_con}}, g_pre_obs, g_pre_x0).
+    g_Xs / g_log_Ws: incoming gradients from the smoothing objective (psvo_ffbsi_backward)."""
     lib = L.load()
     obs, pre_obs, pre_x0 = _f32(obs, "obs"), _f32(pre_obs, "pre_obs"), _f32(pre_x0, "pre_x0")
     B, T, Dy = obs.shape
@@ -165,21 +189,7 @@ def smc_backward_raw(P: dict, flags: int, obs, pre_obs, pre_x0, N, eps, seed, se
     ps = params_struct(P, keep)
     Dobs = pre_obs.shape[-1] if pre_obs is not None else 0
     dims = make_dims(N, B, T, Dx, Dy, Dobs, pre_x0.shape[-1], flags, seq_offset=seq_offset)
-    gs = L.psvo_grads()
-    grads = {}
-    for name in DIST_NAMES:
-        dp = P.get(name)
-        if dp is None:
-            continue
-        gW = [torch.zeros(w.shape, device=dev, dtype=torch.float32) for w in dp.Ws]
-        gb = [torch.zeros(b.shape, device=dev, dtype=torch.float32) for b in dp.bs]
-        gsc = None if dp.sigma_con is None else torch.zeros(dp.sigma_con.shape, device=dev, dtype=torch.float32)
-        gd = getattr(gs, name)
-        for k in range(len(gW)):
-            gd.net.W[k], gd.net.b[k] = gW[k].data_ptr(), gb[k].data_ptr()
-        if gsc is not None:
-            gd.sigma_con = gsc.data_ptr()
-        grads[name] = dict(W=gW, b=gb, sigma_con=gsc)
+    gs, grads = alloc_grads(P, dev, grads_into)
     g_pre_obs = torch.zeros_like(pre_obs) if pre_obs is not None else None
     g_pre_x0 = torch.zeros_like(pre_x0)
     g_logZ_b = _f32(g_logZ_b, "g_logZ_b")
@@ -189,7 +199,7 @@ def smc_backward_raw(P: dict, flags: int, obs, pre_obs, pre_x0, N, eps, seed, se
         rc = lib.psvo_smc_backward(C.byref(dims), C.byref(ps), _ptr(obs), _ptr(pre_obs), _ptr(pre_x0),
                                    _ptr(_f32(eps, "eps")), C.c_uint64(seed & (2 ** 64 - 1)),
                                    _ptr(Xs), _ptr(X_anc), _ptr(anc), _ptr(log_Ws), _ptr(lse), _ptr(g_logZ_b),
-                                   C.byref(gs), _ptr(g_pre_obs), _ptr(g_pre_x0), _ptr(ws), C.c_size_t(ws.numel()),
+                                   _ptr(_f32(g_Xs, "g_Xs")), _ptr(_f32(g_log_Ws, "g_log_Ws")), C.byref(gs), _ptr(g_pre_obs), _ptr(g_pre_x0), _ptr(ws), C.c_size_t(ws.numel()),
                                    _stream())
     L.check(rc, "psvo_smc_backward")
     return dict(grads=grads, g_pre_obs=g_pre_obs, g_pre_x0=g_pre_x0)
@@ -239,6 +249,37 @@ def ffbsi_forward_raw(P: dict, flags: int, obs, bs_feat, pre_x0, Xs, log_Ws, lse
                                     _stream())
     L.check(rc, "psvo_ffbsi_forward")
     return out
+
+
+def ffbsi_backward_raw(P: dict, flags: int, obs, bs_feat, pre_x0, Xs, log_Ws, lse, M, fwd: dict, g_logZ_b,
+                       eps_bw=None, seed=0, seq_offset=0, grads_into=None):
+    """psvo_ffbsi_backward.  `fwd` = the dict psvo_ffbsi_forward returned.  Returns dict(grads, g_bs_feat, g_pre_x0,
+    g_Xs, g_log_Ws)."""
+    lib = L.load()
+    obs, bs_feat, pre_x0 = _f32(obs, "obs"), _f32(bs_feat, "bs_feat"), _f32(pre_x0, "pre_x0")
+    Xs, log_Ws, lse = _f32(Xs, "Xs"), _f32(log_Ws, "log_Ws"), _f32(lse, "lse")
+    B, T, N, Dx = Xs.shape
+    dev = obs.device
+    keep = []
+    ps = params_struct(P, keep)
+    dims = make_dims(N, B, T, Dx, obs.shape[-1], 0, pre_x0.shape[-1], flags, M=M, Dfeat=bs_feat.shape[-1],
+                     seq_offset=seq_offset)
+    wr = bool(flags & L.F_WITH_RESAMPLING)
+    gs, grads = alloc_grads(P, dev, grads_into)
+    g_bs_feat, g_pre_x0 = torch.zeros_like(bs_feat), torch.zeros_like(pre_x0)
+    g_Xs, g_log_Ws = torch.empty_like(Xs), torch.empty_like(log_Ws)
+    oa = fwd["bw_log_W"] if wr else fwd["Omega"]
+    wsb = lib.psvo_ffbsi_backward_workspace_bytes(C.byref(dims), C.byref(ps))
+    ws = torch.empty(max(wsb, 256), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        rc = lib.psvo_ffbsi_backward(C.byref(dims), C.byref(ps), _ptr(obs), _ptr(bs_feat), _ptr(pre_x0), _ptr(Xs),
+                                     _ptr(log_Ws), _ptr(lse), _ptr(_f32(eps_bw, "eps_bw")), C.c_uint64(seed & (2 ** 64 - 1)),
+                                     _ptr(fwd["bw_Xs"]), _ptr(fwd["pick"]), _ptr(fwd.get("f_lp")), _ptr(fwd.get("g_lp")),
+                                     _ptr(oa), _ptr(fwd.get("bw_X_anc")), _ptr(fwd.get("anc2")),
+                                     _ptr(_f32(g_logZ_b, "g_logZ_b")), C.byref(gs), _ptr(g_bs_feat), _ptr(g_pre_x0),
+                                     _ptr(g_Xs), _ptr(g_log_Ws), _ptr(ws), C.c_size_t(ws.numel()), _stream())
+    L.check(rc, "psvo_ffbsi_backward")
+    return dict(grads=grads, g_bs_feat=g_bs_feat, g_pre_x0=g_pre_x0, g_Xs=g_Xs, g_log_Ws=g_log_Ws)
 
 
 # ----------------------------------------------------------------------------------------------------

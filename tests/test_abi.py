@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_error_text(lib):
-    assert lib.psvo_version() == 100
+    assert lib.psvo_version() == 200
     rc = lib.psvo_resample(None, None, 1, 4, 4, None, None)
     assert rc < 0 and b"null" in lib.psvo_last_error()
 

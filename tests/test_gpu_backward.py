@@ -105,3 +105,126 @@ def test_facade_training_step_reduces_loss():
         opt.step()
     assert float(log_ZSMC) > first + 1.0, (first, float(log_ZSMC))
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+# ------------------------------------------------------------------------------------------------------
+# smoothing objectives (PSVO / PSVOwR): psvo_ffbsi_backward chained into psvo_smc_backward
+# ------------------------------------------------------------------------------------------------------
+SMOOTH_CASES = [
+    # name, Dx, Dy, Dfeat, hidden, N, M, B, T, wr, flags
+    ("psvo_small", 2, 1, 6, [8], 16, 4, 2, 4, False, O.Flags()),
+    ("psvo_c2_shape", 3, 3, 16, [32], 64, 8, 2, 5, False, O.Flags()),
+    ("psvowr_small", 3, 2, 8, [16], 40, 4, 2, 5, True, O.Flags()),
+    ("psvo_linear_poisson", 4, 1, 8, [], 48, 5, 2, 4, False, O.Flags(poisson_emission=True)),
+    ("psvo_noboot", 2, 2, 4, [8], 33, 3, 2, 4, False, O.Flags(use_bootstrap=False)),
+    ("psvowr_no2q", 2, 2, 4, [8], 32, 4, 2, 4, True, O.Flags(use_2_q=False)),
+    ("psvo_c5_shape", 16, 32, 16, [64], 32, 4, 1, 3, False, O.Flags()),
+    ("psvo_T2", 2, 1, 4, [8], 16, 4, 2, 2, False, O.Flags()),
+]
+
+
+def smooth_leaves_of(P):
+    out = []
+    for name in ("q0", "q1", "q2", "f", "g", "bsim_q_init", "q1_inv", "bsim_q2"):
+        d = getattr(P, name)
+        if d is None:
+            continue
+        for k, (w, b) in enumerate(zip(d.net.W, d.net.b)):
+            out += [("%s.W%d" % (name, k), w), ("%s.b%d" % (name, k), b)]
+        if d.sigma_con is not None:
+            out.append((name + ".sigma_con", d.sigma_con))
+    return out
+
+
+@pytest.mark.parametrize("cfg", SMOOTH_CASES, ids=[c[0] for c in SMOOTH_CASES])
+def test_smoothing_gradients_vs_oracle_autograd(cfg):
+    """d(sum_b w_b logZ_b)/d(everything) of the PSVO / PSVOwR objective: kernels vs fp64 autograd of the oracle,
+    teacher-forced on the kernels' own ancestors, picks and second-resampling indices."""
+    from psvo_b200 import ops
+    name, Dx, Dy, Dfeat, hidden, N, M, B, T, wr, F = cfg
+    Dx0 = Dy if (F.use_bootstrap and F.use_2_q) else Dx
+    P = O.make_params(5, Dx, Dy, Dy, Dx0, hidden, F, ffbsi=True, Dfeat=Dfeat)
+    g = torch.Generator().manual_seed(21)
+    obs = O.simulate_obs(P, F, B, T)
+    pre_obs = obs.clone()
+    pre_x0 = torch.randn(B, Dx0, generator=g)
+    eps = torch.randn(B, T, N, Dx, generator=g)
+    u = torch.rand(B, T, N, generator=g)
+    bs_feat = torch.randn(B, T, Dfeat, generator=g)
+    eps_bw = torch.randn(B, T, M, N, Dx, generator=g)
+    u_pick, u_res = torch.rand(B, T, N, generator=g), torch.rand(B, T, N, generator=g)
+
+    Pd = to_dev(P)
+    for dp in Pd.values():
+        for t in dp.tensors():
+            t.requires_grad_(True)
+    pre_obs_d = pre_obs.to(DEV).requires_grad_(True)
+    pre_x0_d = pre_x0.to(DEV).requires_grad_(True)
+    feat_d = bs_feat.to(DEV).requires_grad_(True)
+    wgt = torch.linspace(0.5, 1.5, B)
+    logZ_b, Xout, last = ops.smoothing_objective(Pd, flags_of(F, wr), obs.to(DEV), pre_obs_d, pre_x0_d, feat_d, N, M,
+                                                 eps=eps.to(DEV), u=u.to(DEV), eps_bw=eps_bw.to(DEV), u_pick=u_pick.to(DEV),
+                                                 u_res=u_res.to(DEV) if wr else None)
+    (logZ_b * wgt.to(DEV)).sum().backward()
+    anc = last["filter"]["anc"].cpu().long()
+    pick = last["bsim"]["pick"].cpu().long()
+    anc2 = last["bsim"]["anc2"].cpu().long() if wr else None
+
+    P64 = O.params_to(P, torch.float64, requires_grad=True)
+    po, px = pre_obs.double().requires_grad_(True), pre_x0.double().requires_grad_(True)
+    pf = bs_feat.double().requires_grad_(True)
+    fw = O.smc_forward(P64, F, obs.double(), po, px, eps.double(), None, forced_anc=anc)
+    ref = O.backward_simulation(P64, F, obs.double(), pf, px, fw["Xs"], fw["log_Ws"], eps_bw.double(), None,
+                                with_resampling=wr, forced_pick=pick, forced_anc2=anc2)
+    assert_close(logZ_b, ref["logZ_b"], 1e-5, 1e-5 * float(ref["logZ_b"].abs().max()), "logZ_b")
+    (ref["logZ_b"] * wgt.double()).sum().backward()
+
+    got = {}
+    for nm, dp in Pd.items():
+        for k, (w, b) in enumerate(zip(dp.Ws, dp.bs)):
+            got["%s.W%d" % (nm, k)], got["%s.b%d" % (nm, k)] = w.grad, b.grad
+        if dp.sigma_con is not None:
+            got[nm + ".sigma_con"] = dp.sigma_con.grad
+    worst, bad = 0.0, []
+    for key, t in smooth_leaves_of(P64):
+        r = t.grad if t.grad is not None else torch.zeros_like(t)
+        gg = got[key] if got[key] is not None else torch.zeros_like(t, dtype=torch.float32, device=DEV)
+        scale = max(float(r.abs().max()), 1e-3)
+        err = float((gg.double().cpu() - r).abs().max()) / scale
+        worst = max(worst, err)
+        if err >= 5e-5:
+            bad.append("%s: max err %.3e of max |grad| %.3e" % (key, err, scale))
+    assert not bad, "; ".join(bad)
+    assert_close(feat_d.grad, pf.grad, 0, 5e-5 * max(float(pf.grad.abs().max()), 1e-3), "g_bs_feat")
+    gx0 = px.grad if px.grad is not None else torch.zeros_like(px)
+    assert_close(pre_x0_d.grad, gx0, 0, 5e-5 * max(float(gx0.abs().max()), 1e-3), "g_pre_x0")
+    if F.use_2_q:
+        assert_close(pre_obs_d.grad, po.grad, 0, 5e-5 * max(float(po.grad.abs().max()), 1e-3), "g_pre_obs")
+    print("%s: worst relative gradient error %.2e" % (name, worst))
+
+
+def test_psvo_facade_training_step_reduces_loss():
+    """PSVO(model, FLAGS).get_log_ZSMC + Adam, the reference's default objective (src/runner_flag.py:103)."""
+    from psvo_b200.flags import default_flags
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.PSVO import PSVO
+    torch.manual_seed(0)
+    F = default_flags(Dx=2, Dy=1, n_particles=32, n_particles_for_BSim_proposal=4, PSVO=True)
+    model = SSM(F)
+    smc = PSVO(model, F)
+    t = torch.arange(20, dtype=torch.float32)
+    obs = torch.stack([torch.sin(0.3 * t + p) for p in (0.0, 1.0, 2.0)])[:, :, None].to(DEV)
+    log_ZSMC, log = smc.get_log_ZSMC(obs, None, seed=1)
+    assert log["Xs"].shape == (3, 20, 32, 2)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+    first = float(log_ZSMC.detach())
+    for it in range(40):
+        opt.zero_grad()
+        log_ZSMC, _ = smc.get_log_ZSMC(obs, None, seed=1)
+        (-log_ZSMC).backward()
+        opt.step()
+    assert float(log_ZSMC.detach()) > first + 1.0, (first, float(log_ZSMC.detach()))
+    got = [p for p in model.parameters() if p.grad is not None]
+    assert len(got) > 10 and all(torch.isfinite(p.grad).all() for p in got)
+    lstm = [p for n, p in model.named_parameters() if "smoother" in n and p.grad is not None]
+    assert lstm and any(float(p.grad.abs().max()) > 0 for p in lstm), "no gradient reached the bi-LSTM encoder"
