@@ -41,6 +41,11 @@ WORKLOADS = {
                    note="BASELINE configs[0] FHN shape, N=64, T=200, B=1 (latency-bound single chain)"),
     "c4_allen": dict(cls="AESMC", Dx=4, Dy=1, H=[64], N=2048, T=1000, B=1, poisson=True,
                      note="BASELINE configs[3] shape, poisson emission, N=2048, T=1000, B=1"),
+    # FFBSi backward simulation (psvo_ffbsi_forward) measured on its own: value = pair evaluations / s
+    "c5_ffbsi": dict(cls="PSVO", Dx=16, Dy=32, H=[256], N=4096, M=16, T=6, B=8, ffbsi=True, Dfeat=64,
+                     note="FFBSi point of BASELINE configs[4] (N=4096, M=16, Dx=16, Dy=32, H=256); T=6, B=8 slice"),
+    "c2_lorenz_psvo": dict(cls="PSVO", Dx=3, Dy=3, H=[32], N=256, M=16, T=500, B=1, ffbsi=True, Dfeat=64,
+                           note="BASELINE configs[1] Lorenz shape, PSVO (FFBSi), N=256, M=16, T=500, B=1 (latency-bound)"),
     "tiny": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=512, T=20, B=8, note="smoke-size config-5 shape"),
 }
 
@@ -258,6 +263,68 @@ def run_ours(args, w, rank, world, local_rank):
     return line
 
 
+def run_ffbsi(args, w, rank, world, local_rank):
+    """psvo_ffbsi_forward alone (filter outputs resident).  value = pair evaluations M*N^2*B*(T-1) per second."""
+    import ctypes as C
+    from psvo_b200 import _lib, functional as Fn
+    from oracle import psvo_oracle as O          # parameter construction only (he_normal init of the right shapes)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import to_dev, flags_of
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, T, N, M, Dx, Dy = w["B"], w["T"], w["N"], w["M"], w["Dx"], w["Dy"]
+    F = O.Flags()
+    P = to_dev(O.make_params(1234, Dx, Dy, Dy, Dy, w["H"], F, ffbsi=True, Dfeat=w["Dfeat"]), dev)
+    obs = synth_obs(w, B, 1234, rank * B).to(dev)
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(B, T, w["Dfeat"], generator=g).to(dev)
+    fw = Fn.smc_forward_raw(P, flags_of(F), obs, obs, obs[:, 0].contiguous(), N, seed=1, seq_offset=rank * B)
+
+    def step(seed):
+        return Fn.ffbsi_forward_raw(P, flags_of(F), obs, feat, obs[:, 0].contiguous(), fw["Xs"], fw["log_Ws"], fw["lse"], M,
+                                    seed=seed, seq_offset=rank * B)
+    for i in range(args.warmup):
+        r = step(i)
+    torch.cuda.synchronize()
+    lib.psvo_profile_read(None, None)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        r = step(100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (C.c_int64 * 8)()
+    lib.psvo_profile_read(None, launches)
+    lib.psvo_profile_enable(1)
+    step(999)
+    torch.cuda.synchronize()
+    kms, kl = (C.c_double * 8)(), (C.c_int64 * 8)()
+    lib.psvo_profile_read(kms, kl)
+    lib.psvo_profile_enable(0)
+    pairs = world * M * N * N * B * (T - 1)
+    peaks, peak_src = read_peaks()
+    rate = pairs / (ms * 1e-3)
+    mufu_peak = 148 * 16 * 1.965e9
+    return {"metric": "pair-evaluations/sec (FFBSi backward simulation, psvo_ffbsi_forward)", "value": rate, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": w["note"], "class": "PSVO", "n_particles": N, "M": M, "T": T,
+                       "batch_per_gpu": B, "Dx": Dx, "Dy": Dy, "mlp_hidden": w["H"], "rng": "in-kernel Philox4x32-10"},
+            "gpu_launches": int(sum(launches)), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": 2 * Dx * rate / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": 2 * Dx * rate / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "kernel": "ffbsi step (pairwise predictive term)", "peak_source": peak_src,
+                         "mufu": {"achieved_ex2_per_s": rate, "peak_ex2_per_s": mufu_peak, "frac": rate / mufu_peak,
+                                  "note": "1 ex2 per pair; 148 SMs x 16/clk x 1.965 GHz"},
+                         "ffbsi_ms_per_pass": kms[5], "ffbsi_launches": int(kl[5])},
+            "log_ZSMC": float(r["logZ_b"].mean())}
+
+
 def cpu_sample(w, budget_s=15.0, threads=None):
     """Time the oracle restatement (PyTorch CPU fp32) on a bounded slice of the workload."""
     from oracle import psvo_oracle as O
@@ -342,6 +409,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if w.get("ffbsi"):
+            line = run_ffbsi(args, w, rank, world, local_rank)
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            return
         line = run_ours(args, w, rank, world, local_rank)
         if rank == 0:
             if world == 1 and not args.no_cpu_baseline:

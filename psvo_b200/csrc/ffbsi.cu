@@ -92,6 +92,7 @@ struct FfbsiArgs {
   const float* X_next;       // (B,T,N,Dx): bw_Xs (PSVO) or bw_X_anc (PSVOwR); slab t+1 is read
   const float* eps_bw; const float* u_pick; const int* forced_pick;
   float* bw_Xs; int* pick; float* out_f; float* out_g; float* out_a; float* omega_pick; float* omega_all;
+  const float* P_ext;        // (B,N,M) pairwise log-sum-exp from the tensor-core kernel, or NULL -> SIMT loop below
   unsigned long long seed;
   int N, M, B, T, Dx, Dy, t, seq_offset, IL;
   unsigned flags;
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     }
     // ---- predictive term
     float P;
-    if (!first) {
+    if (!first && a.P_ext != nullptr) {
+      P = a.P_ext[((size_t)b * N + ii) * M + (live ? m : 0)] - lds[1] - cx;
+    } else if (!first) {
       float xs[DXP];
 #pragma unroll
       for (int d = 0; d < DXP; ++d) xs[d] = d < Dx ? X[0][d] / sf[d] : 0.0f;
@@ -355,7 +358,7 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick; size_t bytes; };
+struct FfWs { float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP; unsigned char* bimg; size_t bytes; };
 static FfWs carve_ff(const psvo_dims* d, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
@@ -364,6 +367,11 @@ static FfWs carve_ff(const psvo_dims* d, char* base) {
   w.mu_f = take(BN * d->Dx); w.mu1i = take(BN * d->Dx);
   w.m2_all = take(BT * d->Dx); w.mu_init_all = take(BT * d->Dx); w.mu0i = take((size_t)d->B * d->Dx);
   w.omega_pick = take(BT * d->N);
+  w.candP = nullptr; w.bimg = nullptr;
+  if (ffbsi_pair_tc_supported(d->N, d->M, d->B, d->Dx)) {
+    w.candP = take(BN * d->M);
+    w.bimg = reinterpret_cast<unsigned char*>(take(ffbsi_pair_tc_image_bytes(d->B, d->N) / sizeof(float)));
+  }
   w.bytes = off;
   return w;
 }
@@ -423,6 +431,12 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   a.eps_bw = eps_bw; a.u_pick = u_pick; a.forced_pick = forced_pick;
   a.bw_Xs = bw_Xs; a.pick = pick; a.out_f = f_lp; a.out_g = g_lp; a.out_a = Omega_or_bw_log_W;
   a.omega_pick = w.omega_pick; a.omega_all = omega_all; a.seed = seed;
+  a.P_ext = nullptr;
+  const bool pair_tc = w.candP != nullptr;
+  PairTcArgs pt;
+  pt.sig = w.sig; pt.mu_f = w.mu_f; pt.mu1i = w.mu1i; pt.m2_all = w.m2_all; pt.mu_init_all = w.mu_init_all;
+  pt.log_Ws = log_Ws; pt.lse = lse; pt.eps_bw = eps_bw; pt.bimg = w.bimg; pt.candP = w.candP; pt.seed = seed;
+  pt.N = N; pt.M = M; pt.B = B; pt.T = T; pt.Dx = Dx; pt.seq_offset = d->seq_offset; pt.flags = d->flags;
   a.N = N; a.M = M; a.B = B; a.T = T; a.Dx = Dx; a.Dy = d->Dy; a.seq_offset = d->seq_offset; a.flags = d->flags;
 
   const int DXP = pad_dx(Dx), DYP = pad_dy(d->Dy);
@@ -458,6 +472,12 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
                     : (DXP == 8 ? launch_particle_mlp<8>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)
                                 : launch_particle_mlp<16>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st));
       if (rc) return rc;
+    }
+    a.P_ext = nullptr;
+    if (pair_tc && t >= 1) {
+      pt.t = t;
+      if ((rc = launch_ffbsi_pair_tc(pt, st))) return rc;
+      a.P_ext = w.candP;
     }
     rc = -1;
 #define PSVO_CASE_F(X, Y) if (DXP == X && DYP == Y) rc = launch_step_t<X, Y>(a, block, grid, smem, st);

@@ -1,0 +1,322 @@
+// ffbsi_pair_tc.cu -- the PAIRWISE predictive term of the FFBSi backward simulation on sm_100a tensor cores.
+//
+// Reference: PSVO.backward_simulation_w_proposal, src/SMC/PSVO.py:89-94,128-133 (and PSVOwR.py:88-93,127-133):
+//     f_tm1_log_prob = f.log_prob(Xs[t-1], tile(bw_X_t))          (M, N, N, B)   <- materialised by tf.tile
+//     log_W_t        = reduce_logsumexp(f_tm1_log_prob + log_W_tm1, axis=2)
+// i.e. for every candidate row r = (i, m) of a sequence:  P[r] = LSE_j( log N(x~_r; mu_j, s_f) + log Wbar_{t-1}[j] ).
+//
+// As a GEMM: with xs = x~/s_f, mus = mu_j/s_f,
+//     log N(...) + log Wbar_j = const + ( xs . mus + c_j ) - |xs|^2 / 2 ,     c_j = log Wbar_j - |mus|^2 / 2
+// rows = candidates (M*N per sequence), columns = filter particles j (N), K = Dx <= 16.  The c_j term rides in the
+// GEMM as two extra K entries (A = 1, B = c_j split hi/lo), the row term is added after the log-sum-exp.
+//
+// Arithmetic: fp16x3 split products (tc_common.cuh) with both operands pre-scaled by 16, fp32 accumulation in TMEM:
+//     D = 256 * (xs . mus + c_j)  =  hi*hi + [256 * c_hi + 256 * c_lo] + hi*lo + lo*hi          (4 MMAs, N = 128)
+//
+// CTA (persistent, one per SM) = 2 compute groups of 128 threads (TMEM lane == candidate row == thread), one
+// MMA-issuing warp, one TMA producer warp:
+//     producer : streams the per-sequence B image (128-column tiles, 12 KB each, prepared by ffbsi_pair_prep_kernel in
+//                the UMMA operand layout) through a 4-stage ring with cp.async.bulk + mbarrier transaction counts;
+//     MMA warp : per column tile and group, 4 tcgen05.mma into a double-buffered 128-column accumulator; tcgen05.commit
+//                releases the B stage and publishes the accumulator;
+//     compute  : build the A operand of their row tile once (recompute the candidate from eps_bw / Philox), then per
+//                column tile tcgen05.ld their row and fold it into an online log-sum-exp (1 ex2 per pair -- the MUFU
+//                pipe, not the tensor pipe, bounds this kernel: 16 ex2/clk/SM).
+// The (M,N,N,B,Dx) tensor never exists; the tile never leaves the SM; HBM traffic is the 4-byte P per candidate.
+#include <stdlib.h>
+#include "smc_kernels.h"
+#include "tc_common.cuh"
+
+namespace psvo {
+
+constexpr int kPtStages = 4;
+constexpr int kPtTileBytes = 12288;      // 128 columns: hi+ext K=32 (4 K-groups x 2 KB) | lo K=16 (2 K-groups x 2 KB)
+constexpr int kPtThreads = 2 * 128 + 64;
+constexpr float kPtScale = 16.0f;        // operand scale (exact); the accumulator holds 256 * (dot + c_j)
+constexpr float kPtSentinel = -60000.0f; // c_j of padded columns / zero-weight particles (finite in fp16)
+
+// ---- B image: per (sequence, 128-column tile) the UMMA B operand [N = 128 rows j][K] ----------------------------
+__global__ void __launch_bounds__(128) ffbsi_pair_prep_kernel(PairTcArgs a) {
+  const int ct = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
+  const int N = a.N, Dx = a.Dx, NT = (N + 127) / 128;
+  const bool boot = a.flags & PSVO_F_BOOTSTRAP;
+  const int j = ct * 128 + r;
+  const bool live = j < N;
+  const size_t btm = (size_t)b * a.T + (a.t - 1);
+  float mus[16];
+  float nrm = 0.0f;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    float v = 0.0f;
+    if (live && d < Dx) v = a.mu_f[((size_t)b * N + j) * Dx + d] / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+    mus[d] = v;
+    nrm = fmaf(v, v, nrm);
+  }
+  float cj = kPtSentinel;
+  if (live) cj = fmaxf((a.log_Ws[btm * N + j] - a.lse[btm]) - 0.5f * nrm, kPtSentinel);
+  unsigned char* img = a.bimg + ((size_t)b * NT + ct) * kPtTileBytes;
+#pragma unroll
+  for (int kg = 0; kg < 2; ++kg) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = mus[kg * 8 + i] * kPtScale;
+    uint4 hi, lo;
+    tc::split8_f16(v, hi, lo);
+    *reinterpret_cast<uint4*>(img + kg * 2048 + r * 16) = hi;
+    *reinterpret_cast<uint4*>(img + 8192 + kg * 2048 + r * 16) = lo;
+  }
+  const __half ch = __float2half_rn(cj);
+  const __half cl = __float2half_rn(cj - __half2float(ch));
+  const __half2 c2 = __halves2half2(ch, cl);
+  *reinterpret_cast<uint4*>(img + 2 * 2048 + r * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&c2), 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(img + 3 * 2048 + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// one MUFU instruction: 2^x, flush-to-zero (arguments are <= 0 here; relative error ~2^-22)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct PtSmem { uint32_t stage, aop, bars, slot, consts, total; };
+__host__ __device__ inline PtSmem pt_layout() {
+  PtSmem s; uint32_t o = 0;
+  s.stage = o; o += kPtStages * kPtTileBytes;
+  s.aop = o; o += 2 * kPtTileBytes;
+  s.bars = o; o += 256;
+  s.slot = o; o += 128;
+  s.consts = o; o += 4 * 16 * 4;
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const PtSmem L = pt_layout();
+  const int N = a.N, M = a.M, T = a.T, t = a.t, Dx = a.Dx;
+  const bool boot = a.flags & PSVO_F_BOOTSTRAP;
+  const bool last = t == T - 1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int NT = (N + 127) / 128;
+  const long long ncand = (long long)N * M;
+  const int rt_per_seq = (int)((ncand + 127) / 128);
+  const int items_per_seq = (rt_per_seq + 1) / 2;
+  const int work = a.B * items_per_seq;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint64_t* full = bars;                    // [S]   B stage loaded        (1 arrival + tx bytes)
+  uint64_t* empty = bars + kPtStages;       // [S]   B stage consumed      (tcgen05.commit)
+  uint64_t* dfull = bars + 2 * kPtStages;   // [g*2+buf] accumulator ready (tcgen05.commit)
+  uint64_t* dempty = dfull + 4;             // [g*2+buf] accumulator read  (128 arrivals)
+  uint64_t* afull = dempty + 4;             // [g]   A operand staged      (128 arrivals)
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
+  float* C = reinterpret_cast<float*>(sm + L.consts);   // sp[16] | inv1[16] | inv2[16] | sf[16]
+
+  if (tid < 16) {
+    const int d = tid;
+    const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
+    C[16 + d] = 1.0f / s1; C[32 + d] = 1.0f / s2;
+    C[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
+    C[48 + d] = a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+  }
+  if (tid == 32) {
+    for (int s = 0; s < kPtStages; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    for (int k = 0; k < 4; ++k) { tc::mbar_init(dfull + k, 1); tc::mbar_init(dempty + k, 128); }
+    tc::mbar_init(afull, 128); tc::mbar_init(afull + 1, 128);
+  }
+  if (warp == 0) tc::tmem_alloc(slot, 512);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *slot;
+
+  if (warp == 9) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        const int b = wi / items_per_seq;
+        const unsigned char* src = a.bimg + (size_t)b * NT * kPtTileBytes;
+        for (int ct = 0; ct < NT; ++ct, ++q) {
+          const uint32_t s = q % kPtStages, ph = (q / kPtStages) & 1u;
+          tc::mbar_wait(empty + s, ph ^ 1u);
+          tc::mbar_arrive_expect_tx(full + s, kPtTileBytes);
+          tc::bulk_g2s(sm + L.stage + s * kPtTileBytes, src + (size_t)ct * kPtTileBytes, kPtTileBytes, full + s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, 128);
+      uint64_t adesc_hi[2], adesc_lo[2];
+      for (int g = 0; g < 2; ++g) {
+        adesc_hi[g] = tc::make_desc(tc::smem_u32(sm + L.aop + g * kPtTileBytes), 2048, 128);
+        adesc_lo[g] = tc::make_desc(tc::smem_u32(sm + L.aop + g * kPtTileBytes + 8192), 2048, 128);
+      }
+      uint32_t q = 0, it = 0;
+      for (int wi = blockIdx.x; wi < work; wi += gridDim.x, ++it) {
+        tc::mbar_wait(afull, it & 1u);
+        tc::mbar_wait(afull + 1, it & 1u);
+        tc::fence_after_sync();
+        for (int ct = 0; ct < NT; ++ct, ++q) {
+          const uint32_t s = q % kPtStages;
+          tc::mbar_wait(full + s, (q / kPtStages) & 1u);
+          tc::fence_after_sync();
+          const uint64_t bhi = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes), 2048, 128);
+          const uint64_t blo = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes + 8192), 2048, 128);
+          const uint32_t buf = q & 1u;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            tc::mbar_wait(dempty + g * 2 + buf, ((q >> 1) & 1u) ^ 1u);
+            tc::fence_after_sync();
+            const uint32_t d = tmem + (uint32_t)(g * 2 + buf) * 128u;
+            tc::mma_bf16(d, adesc_hi[g], bhi, idesc, false);                          // hi * hi
+            tc::mma_bf16(d, adesc_hi[g] + (4096 >> 4), bhi + (4096 >> 4), idesc, true);   // 256 * (c_hi + c_lo)
+            tc::mma_bf16(d, adesc_hi[g], blo, idesc, true);                           // hi * lo
+            tc::mma_bf16(d, adesc_lo[g], bhi, idesc, true);                           // lo * hi
+            tc::mma_commit(dfull + g * 2 + buf);
+          }
+          tc::mma_commit(empty + s);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ compute groups ================================
+    const int g = warp >> 2;
+    const int gt = tid & 127;
+    const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* sf = C + 48;
+    unsigned char* pa = sm + L.aop + g * kPtTileBytes + gt * 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float kexp = 1.4426950408889634f / (kPtScale * kPtScale);
+    uint32_t q = 0;
+    for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+      const int b = wi / items_per_seq;
+      const int rt = (wi - b * items_per_seq) * 2 + g;
+      const long long c = (long long)rt * 128 + gt;
+      const bool live = rt < rt_per_seq && c < ncand;
+      const int i = live ? (int)(c / M) : 0, m = live ? (int)(c - (long long)i * M) : 0;
+      const size_t bt = (size_t)b * T + t;
+
+      // ---- candidate x~ = mean + sp * eps (same arithmetic as ffbsi_step_kernel), scaled by 1 / s_f
+      float xs[16];
+      float rr = 0.0f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * cc < Dx) {
+          if (a.eps_bw != nullptr) {
+            const float* src = a.eps_bw + (((bt * M + m) * N + i) * (size_t)Dx);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (4 * cc + k < Dx) e[k] = src[4 * cc + k];
+          } else {
+            const uint64_t gidx = ((((uint64_t)(a.seq_offset + b) * T + t) * M + m) * N) + i;
+            normal4(philox4x32_10(a.seed, gidx, cc, 2u), e);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = 4 * cc + k;
+          float xv = 0.0f;
+          if (d < Dx && live) {
+            float mean;
+            if (last) mean = a.mu_init_all[bt * Dx + d];
+            else {
+              const float m1 = a.mu1i[((size_t)b * N + i) * Dx + d], m2 = a.m2_all[bt * Dx + d];
+              mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
+            }
+            xv = (mean + sp[d] * e[k]) / sf[d];
+          }
+          xs[d] = xv;
+          rr = fmaf(xv, xv, rr);
+        }
+      }
+      rr *= -0.5f;
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = xs[kg * 8 + k] * kPtScale;
+        uint4 hi, lo;
+        tc::split8_f16(v, hi, lo);
+        *reinterpret_cast<uint4*>(pa + kg * 2048) = hi;
+        *reinterpret_cast<uint4*>(pa + 8192 + kg * 2048) = lo;
+      }
+      {
+        const __half2 one2 = __floats2half2_rn(kPtScale * kPtScale, kPtScale * kPtScale);
+        const uint32_t o = live ? *reinterpret_cast<const uint32_t*>(&one2) : 0u;
+        *reinterpret_cast<uint4*>(pa + 2 * 2048) = make_uint4(o, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(pa + 3 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      tc::mbar_arrive(afull + g);
+
+      // ---- online log-sum-exp over the column tiles (accumulator units: 256 * natural log)
+      float mD = -INFINITY, sum = 0.0f;
+      for (int ct = 0; ct < NT; ++ct, ++q) {
+        const uint32_t buf = q & 1u;
+        tc::mbar_wait(dfull + g * 2 + buf, (q >> 1) & 1u);
+        tc::fence_after_sync();
+        const uint32_t td = tmem + (uint32_t)(g * 2 + buf) * 128u + lane_base;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          tc::tmem_ld32(td + cc * 32, v);
+          float cm = v[0];
+#pragma unroll
+          for (int k = 1; k < 32; ++k) cm = fmaxf(cm, v[k]);
+          if (cm > mD) { sum *= fast_ex2((mD - cm) * kexp); mD = cm; }
+          const float off = -mD * kexp;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) { s0 += fast_ex2(fmaf(v[k], kexp, off)); s1 += fast_ex2(fmaf(v[k + 1], kexp, off)); }
+          sum += s0 + s1;
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(dempty + g * 2 + buf);
+      }
+      if (live) a.candP[(size_t)b * ncand + c] = (mD * (1.0f / (kPtScale * kPtScale)) + logf(sum)) + rr;
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+bool ffbsi_pair_tc_supported(int N, int M, int B, int Dx) {
+  static const bool disabled = getenv("PSVO_DISABLE_TC") != nullptr && getenv("PSVO_DISABLE_TC")[0] == '1';
+  if (disabled || Dx > 16) return false;
+  // one CTA item = 256 candidate rows x all N columns; below a machine-filling amount of work the SIMT loop wins
+  return N >= 128 && (long long)B * N * M >= 2048;
+}
+
+size_t ffbsi_pair_tc_image_bytes(int B, int N) { return (size_t)B * ((N + 127) / 128) * kPtTileBytes; }
+
+int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
+  const int NT = (a.N + 127) / 128;
+  {
+    ProfScope ps_(PK_FFBSI, st);
+    ffbsi_pair_prep_kernel<<<dim3(NT, a.B), 128, 0, st>>>(a);
+    PSVO_LAUNCH_CHECK();
+  }
+  const PtSmem L = pt_layout();
+  const size_t smem = L.total + 128;
+  static bool cfg = false;
+  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(ffbsi_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+  const long long ncand = (long long)a.N * a.M;
+  const long long work = (long long)a.B * (((ncand + 127) / 128 + 1) / 2);
+  const int grid = (int)(work < num_sms() ? work : num_sms());
+  ProfScope ps_(PK_FFBSI, st);
+  ffbsi_pair_tc_kernel<<<grid, kPtThreads, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace psvo

@@ -62,6 +62,20 @@ int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g
 int launch_particle_mlp_dx(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, int Dx, float* out,
                            cudaStream_t st);
 
+// tensor-core (tcgen05) pairwise predictive term of the FFBSi backward simulation (ffbsi_pair_tc.cu)
+struct PairTcArgs {
+  const float* sig; const float* mu_f; const float* mu1i; const float* m2_all; const float* mu_init_all;
+  const float* log_Ws; const float* lse; const float* eps_bw;
+  unsigned char* bimg;     // B image workspace, ffbsi_pair_tc_image_bytes()
+  float* candP;            // (B, N, M) out: LSE_j( -|x~/s - mu_j/s|^2 / 2 + log Wbar_j )
+  unsigned long long seed;
+  int N, M, B, T, Dx, t, seq_offset;
+  unsigned flags;
+};
+bool ffbsi_pair_tc_supported(int N, int M, int B, int Dx);
+size_t ffbsi_pair_tc_image_bytes(int B, int N);
+int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st);
+
 // tensor-core (tcgen05) propagate step (smc_propagate_tc.cu)
 bool tc_propagate_supported(const PropArgs& a);
 size_t tc_image_bytes(const PropArgs& a);

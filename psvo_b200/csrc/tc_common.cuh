@@ -134,6 +134,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
 
+// producer side of a transaction barrier: one arrival + `bytes` expected from bulk copies
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, size multiple of 16, 16-byte aligned), completion counted on `mbar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------------------
 // 8 consecutive k of one row -> two 16-byte chunks (hi, lo)
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {

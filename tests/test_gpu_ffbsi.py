@@ -57,6 +57,11 @@ BS_CONFIGS = [
     ("c5_shape_small", 16, 32, 64, [256], 128, 4, 1, 3, False, O.Flags()),
     ("linear_poisson", 4, 1, 8, [], 64, 5, 2, 4, False, O.Flags(poisson_emission=True)),
     ("noboot_wr", 2, 2, 4, [8], 50, 4, 2, 4, True, O.Flags(use_bootstrap=False)),
+    # sizes that take the tcgen05 pairwise kernel (N >= 128 and B*N*M >= 2048): ragged row / column tiles, Dx = 16
+    ("tc_pair_ragged", 3, 2, 8, [16], 300, 5, 2, 4, False, O.Flags()),
+    ("tc_pair_dx16", 16, 32, 16, [64], 256, 8, 1, 3, False, O.Flags()),
+    ("tc_pair_wr", 4, 2, 8, [16], 200, 6, 2, 4, True, O.Flags()),
+    ("tc_pair_many_tiles", 2, 1, 8, [8], 640, 4, 3, 3, False, O.Flags()),
 ]
 
 
