@@ -93,6 +93,7 @@ struct FfbsiArgs {
   const float* eps_bw; const float* u_pick; const int* forced_pick;
   float* bw_Xs; int* pick; float* out_f; float* out_g; float* out_a; float* omega_pick; float* omega_all;
   const float* P_ext;        // (B,N,M) pairwise log-sum-exp from the tensor-core kernel, or NULL -> SIMT loop below
+  const float* F_ext; const float* G_ext;   // (B,N,M) f_lp / g_lp of every candidate from ffbsi_cand_tc_kernel, or NULL
   unsigned long long seed;
   int N, M, B, T, Dx, Dy, t, seq_offset, IL;
   unsigned flags;
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
   float* sp = p; p += DXP;  float* inv1 = p; p += DXP;  float* inv2 = p; p += DXP;
   float* sf = p; p += DXP;  float* sinit = p; p += DXP; float* sg = p; p += 32;
   float* lds = p; p += 4;                     // logdet: proposal, f, g, init
-  if (!last) p = mlp_stage<DXP, DXP>(a.f, p, fs);
-  p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  const bool ext = a.F_ext != nullptr;        // candidate densities precomputed on tensor cores: no networks staged here
+  if (!last && !ext) p = mlp_stage<DXP, DXP>(a.f, p, fs);
+  if (!ext) p = mlp_stage<DXP, DYP>(a.g, p, gs);
   float* sMu = p; p += kPairChunk * DXP;      // mu_f[j] / s_f
   float* sWb = p; p += kPairChunk;            // normalised log weight of j
   float* sCand = p; p += blockDim.x * 5;      // omega | f | g | q | P per candidate
@@ -190,7 +192,9 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
 
     // ---- f(x_{t+1} | x~)  (MLP f on the candidate)
     float f_lp = 0.0f;
-    if (!last) {
+    if (ext) {
+      f_lp = last ? 0.0f : a.F_ext[((size_t)b * N + ii) * M + (live ? m : 0)];
+    } else if (!last) {
       float muf[1][DXP];
       mlp_eval<DXP, DXP, 1>(fs, X, muf, nullptr, 0);
       float s = 0.f;
@@ -200,7 +204,9 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     }
     // ---- g(y_t | x~)
     float g_lp;
-    {
+    if (ext) {
+      g_lp = a.G_ext[((size_t)b * N + ii) * M + (live ? m : 0)];
+    } else {
       float mug[1][DYP];
       mlp_eval<DXP, DYP, 1>(gs, X, mug, nullptr, 0);
       float s = 0.f;
@@ -358,8 +364,8 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP; unsigned char* bimg; size_t bytes; };
-static FfWs carve_ff(const psvo_dims* d, char* base) {
+struct FfWs { float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG; unsigned char *bimg, *tc_image; size_t bytes; };
+static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
   const size_t BT = (size_t)d->B * d->T, BN = (size_t)d->B * d->N;
@@ -371,6 +377,14 @@ static FfWs carve_ff(const psvo_dims* d, char* base) {
   if (ffbsi_pair_tc_supported(d->N, d->M, d->B, d->Dx)) {
     w.candP = take(BN * d->M);
     w.bimg = reinterpret_cast<unsigned char*>(take(ffbsi_pair_tc_image_bytes(d->B, d->N) / sizeof(float)));
+  }
+  w.candF = w.candG = nullptr; w.tc_image = nullptr;
+  if (p != nullptr) {
+    const psvo_mlp& fnet = (d->flags & PSVO_F_BOOTSTRAP) ? p->q1.net : p->f.net;
+    if (ffbsi_cand_tc_supported(fnet, p->g.net, d->Dx, d->Dy, (long long)BN * d->M)) {
+      w.candF = take(BN * d->M); w.candG = take(BN * d->M);
+      w.tc_image = reinterpret_cast<unsigned char*>(take(32 * 1024));
+    }
   }
   w.bytes = off;
   return w;
@@ -385,7 +399,7 @@ extern "C" {
 PSVO_API size_t psvo_ffbsi_workspace_bytes(const psvo_dims* d, const psvo_params* p) {
   (void)p;
   if (d == nullptr) return 0;
-  return carve_ff(d, nullptr).bytes;
+  return carve_ff(d, p, nullptr).bytes;
 }
 
 PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const float* obs, const float* bs_feat,
@@ -413,7 +427,7 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   PSVO_REQUIRE(obs && bs_feat && pre_x0 && Xs && log_Ws && lse && bw_Xs && pick && Omega_or_bw_log_W && logZ_b && ws,
                "psvo_ffbsi_forward: null buffer");
   PSVO_REQUIRE(wr ? (bw_X_anc && anc2) : (f_lp && g_lp), "psvo_ffbsi_forward: missing %s outputs", wr ? "PSVOwR" : "PSVO");
-  const FfWs w = carve_ff(d, static_cast<char*>(ws));
+  const FfWs w = carve_ff(d, p, static_cast<char*>(ws));
   PSVO_REQUIRE(ws_bytes >= w.bytes, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int B = d->B, T = d->T, N = d->N, M = d->M, Dx = d->Dx;
@@ -439,13 +453,28 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   pt.N = N; pt.M = M; pt.B = B; pt.T = T; pt.Dx = Dx; pt.seq_offset = d->seq_offset; pt.flags = d->flags;
   a.N = N; a.M = M; a.B = B; a.T = T; a.Dx = Dx; a.Dy = d->Dy; a.seq_offset = d->seq_offset; a.flags = d->flags;
 
+  // candidate MLPs f and g on tensor cores (one fp16 weight image per pass, f in the "q" slot)
+  a.F_ext = nullptr; a.G_ext = nullptr;
+  const bool cand_tc = w.candF != nullptr;
+  CandTcArgs ca;
+  if (cand_tc) {
+    PropArgs ia;
+    ia.q1 = fd.net; ia.f = fd.net; ia.g = p->g.net; ia.Dx = Dx; ia.Dy = d->Dy;
+    if (int e = launch_tc_stage_image(ia, w.tc_image, st)) return e;
+    ca.tc_image = w.tc_image; ca.sig = w.sig; ca.obs = obs; ca.mu1i = w.mu1i; ca.m2_all = w.m2_all; ca.mu_init_all = w.mu_init_all;
+    ca.X_next = a.X_next; ca.eps_bw = eps_bw; ca.candF = w.candF; ca.candG = w.candG; ca.seed = seed;
+    ca.N = N; ca.M = M; ca.B = B; ca.T = T; ca.Dx = Dx; ca.Dy = d->Dy; ca.H = p->g.net.width[0]; ca.seq_offset = d->seq_offset;
+    ca.flags = d->flags;
+    a.F_ext = w.candF; a.G_ext = w.candG;
+  }
+
   const int DXP = pad_dx(Dx), DYP = pad_dy(d->Dy);
   int IL = 256 / M; if (IL < 1) IL = 1;
   if (IL > N) IL = N;
   int block = ((IL * M + 31) / 32) * 32;
   a.IL = IL;
   const size_t smem = (5 * DXP + 32 + 4 + kPairChunk * DXP + kPairChunk + (size_t)block * 5 + (size_t)block * DXP) * sizeof(float) +
-                      staged_bytes(a.f, DXP, DXP) + staged_bytes(a.g, DXP, DYP);
+                      (cand_tc ? 0 : staged_bytes(a.f, DXP, DXP) + staged_bytes(a.g, DXP, DYP));
   PSVO_REQUIRE(smem <= 227 * 1024, "psvo_ffbsi_forward: networks too large for shared memory (%zu B)", smem);
   const int64_t work = (int64_t)B * ((N + IL - 1) / IL);
   const int64_t cap = (int64_t)num_sms() * (smem > 100 * 1024 ? 1 : 2);
@@ -472,6 +501,10 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
                     : (DXP == 8 ? launch_particle_mlp<8>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)
                                 : launch_particle_mlp<16>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st));
       if (rc) return rc;
+    }
+    if (cand_tc) {
+      ca.t = t;
+      if ((rc = launch_ffbsi_cand_tc(ca, st))) return rc;
     }
     a.P_ext = nullptr;
     if (pair_tc && t >= 1) {

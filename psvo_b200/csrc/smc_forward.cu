@@ -294,18 +294,23 @@ int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2: normalise + resample + gather.  One CTA per sequence.
-// shared memory: N floats (log weights) + N uint64 (inclusive fixed-point CDF) + scratch
+// K2: normalise + resample + gather.  gridDim = (B, parts): every CTA of a sequence rebuilds the sequence's CDF
+// (N deterministic exps + one integer block scan -- cheap) and serves the children [part*chunk, (part+1)*chunk), so the
+// dependent search + gather chains of one sequence spread over several SMs when B alone cannot fill the machine.
+// shared memory: N uint64 (inclusive fixed-point CDF) + N floats (log weights) + chunk ints (ancestors of this part)
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = a.N, Dx = a.Dx;
   unsigned long long* sC = reinterpret_cast<unsigned long long*>(smraw);
   float* sLW = reinterpret_cast<float*>(sC + N);
+  int* sAnc = reinterpret_cast<int*>(sLW + N);
   __shared__ unsigned long long sscr[33];
   __shared__ float fscr[33];
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, part = blockIdx.y;
+  const int chunk = (N + gridDim.y - 1) / gridDim.y;
+  const int n_lo = min(part * chunk, N), n_hi = min(n_lo + chunk, N);
   const size_t bt = (size_t)b * a.T + a.t;
   const float* lw = a.log_Ws + bt * N;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -314,67 +319,150 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
   for (int i = tid; i < N; i += nt) { const float v = lw[i]; sLW[i] = v; mx = fmaxf(mx, v); }
   mx = block_max(mx, fscr);
 
-  // contiguous chunk per thread: local inclusive scan of the integer weights, then block offsets
-  const int ipt = (N + nt - 1) / nt;
-  const int lo = min(tid * ipt, N), hi = min(lo + ipt, N);
-  unsigned long long run = 0ull;
-  for (int i = lo; i < hi; ++i) { run += fixed_weight(sLW[i], mx); sC[i] = run; }
-  unsigned long long total;
-  const unsigned long long off = block_exscan_u64(run, sscr, &total);
-  for (int i = lo; i < hi; ++i) sC[i] += off;
+  // integer CDF: every warp owns a contiguous run of the particles and walks it 32 at a time (lane = particle:
+  // conflict-free shared-memory rows), warp-shuffle inclusive scan + running carry; then the warp totals are scanned
+  // and added back.  Integer addition is associative, so the CDF does not depend on this decomposition.
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int per_warp = (((N + nw - 1) / nw) + 31) & ~31;
+  const int w_lo = min(wid * per_warp, N), w_hi = min(w_lo + per_warp, N);
+  unsigned long long carry = 0ull;
+  for (int base = w_lo; base < w_hi; base += 32) {
+    const int i = base + lane;
+    unsigned long long v = i < w_hi ? fixed_weight(sLW[i], mx) : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long nb = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += nb;
+    }
+    v += carry;
+    if (i < w_hi) sC[i] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) sscr[wid] = carry;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned long long wt = lane < nw ? sscr[lane] : 0ull;
+    unsigned long long inc = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += nb;
+    }
+    if (lane < nw) sscr[lane] = inc - wt;           // exclusive warp offsets
+    if (lane == 31) sscr[32] = inc;                  // grand total
+  }
+  __syncthreads();
+  const unsigned long long total = sscr[32];
+  const unsigned long long off = sscr[wid];
+  if (off != 0ull) for (int i = w_lo + lane; i < w_hi; i += 32) sC[i] += off;
   __syncthreads();
 
   // logsumexp from the same integer total: deterministic and independent of the thread count
   const float lse = mx + (logf((float)total) - 32.0f * kLn2);
-  if (tid == 0) {
+  if (tid == 0 && part == 0) {
     if (a.lse != nullptr) a.lse[bt] = lse;
     if (a.logZ_b != nullptr) a.logZ_b[b] = (a.t == 0 ? 0.0f : a.logZ_b[b]) + lse;
   }
 
   const bool resample = a.flags & PSVO_F_RESAMPLE;
+  int top = 1;                                   // largest power of two <= N
+  while (top * 2 <= N) top *= 2;
+  // four children per thread at a time: their branch-free binary searches interleave, hiding the shared-memory latency
+  for (int n0 = n_lo + tid; n0 < n_hi; n0 += 4 * nt) {
+    unsigned long long thr[4];
+    int anc[4];
+    bool search[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int n = n0 + k * nt;
+      anc[k] = n; search[k] = false; thr[k] = 0ull;
+      if (n < n_hi && resample) {
+        if (a.forced_anc != nullptr) {
+          const int f = a.forced_anc[bt * N + n];
+          anc[k] = f < 0 ? 0 : (f >= N ? N - 1 : f);
+        } else {
+          uint32_t u24;
+          if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
+          else {
+            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + n;
+            u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
+          }
+          thr[k] = draw_threshold(total, u24);
+          search[k] = true;
+        }
+      }
+    }
+    // #{j : C[j] <= thr} (upper bound) by descending powers of two; identical to upper_bound_u64 on a monotone CDF
+    int pos[4] = {0, 0, 0, 0};
+    for (int s = top; s > 0; s >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cand = pos[k] + s;
+        if (search[k] && cand <= N && sC[cand - 1] <= thr[k]) pos[k] = cand;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int n = n0 + k * nt;
+      if (n >= n_hi) continue;
+      if (search[k]) anc[k] = pos[k] < N ? pos[k] : N - 1;
+      if (!resample) a.logWbar[(size_t)b * N + n] = sLW[n] - lse;      // SVO.py:102,156 (IWAE keeps it differentiable)
+      a.anc[bt * N + n] = anc[k];
+      sAnc[n - n_lo] = anc[k];
+    }
+  }
+  __syncthreads();
+
+  // ancestor gather X_anc[t][n] = X_t[anc[n]]: consecutive threads write consecutive 16-byte pieces of the children
   const float* Xt = a.Xs + bt * N * Dx;
   float* Xa = a.X_anc + bt * N * Dx;
-  for (int n = tid; n < N; n += nt) {
-    int anc = n;
-    if (resample) {
-      if (a.forced_anc != nullptr) {
-        anc = a.forced_anc[bt * N + n];
-        anc = anc < 0 ? 0 : (anc >= N ? N - 1 : anc);
-      } else {
-        uint32_t u24;
-        if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
-        else {
-          const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + n;
-          u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
-        }
-        anc = upper_bound_u64(sC, N, draw_threshold(total, u24));
+  const int nchild = n_hi - n_lo;
+  if ((Dx & 3) == 0) {
+    const int v4 = Dx >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(Xt);
+    float4* dst4 = reinterpret_cast<float4*>(Xa) + (size_t)n_lo * v4;
+    const int pieces = nchild * v4;
+    // four independent row reads in flight per thread before the first store (the loop is latency-bound otherwise)
+    for (int q0 = tid; q0 < pieces; q0 += 4 * nt) {
+      float4 r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = q0 + k * nt;
+        if (q < pieces) { const int c = q / v4, v = q - c * v4; r[k] = __ldg(src4 + (size_t)sAnc[c] * v4 + v); }
       }
-    } else {
-      a.logWbar[(size_t)b * N + n] = sLW[n] - lse;           // SVO.py:102,156 (IWAE keeps it differentiable)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = q0 + k * nt;
+        if (q < pieces) dst4[q] = r[k];
+      }
     }
-    a.anc[bt * N + n] = anc;
-    const float* src = Xt + (size_t)anc * Dx;
-    float* dst = Xa + (size_t)n * Dx;
-    if ((Dx & 3) == 0) {
-      for (int v = 0; v < Dx / 4; ++v) reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
-    } else {
-      for (int d = 0; d < Dx; ++d) dst[d] = src[d];
+  } else {
+    const int pieces = nchild * Dx;
+    float* dst = Xa + (size_t)n_lo * Dx;
+    for (int q = tid; q < pieces; q += nt) {
+      const int c = q / Dx, d = q - c * Dx;
+      dst[q] = Xt[(size_t)sAnc[c] * Dx + d];
     }
   }
 }
 
 int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   const int N = a.N;
+  // CTAs per sequence: enough to put ~2 CTAs on every SM, at least 512 children each
+  int parts = 1;
+  while (parts < 4 && (long long)a.B * parts < 2LL * num_sms() && N / (parts * 2) >= 512) parts *= 2;
+  while (parts < 64 && (size_t)N * 12 + (size_t)((N + parts - 1) / parts) * 4 > 220 * 1024) parts *= 2;   // ancestor scratch must fit
+  const int chunk = (N + parts - 1) / parts;
   int block = N >= 4096 ? 512 : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));
-  const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float));
-  PSVO_REQUIRE(smem <= 200 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 200 KiB)", N, smem);
+  const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float)) + (size_t)chunk * sizeof(int);
+  PSVO_REQUIRE(smem <= 220 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 220 KiB)", N, smem);
   static size_t configured = 0;
   if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(smc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   ProfScope ps_(PK_RESAMPLE, st);
-  smc_resample_kernel<<<a.B, block, smem, st>>>(a);
+  smc_resample_kernel<<<dim3(a.B, parts), block, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
   return 0;
 }

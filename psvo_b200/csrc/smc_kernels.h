@@ -82,6 +82,19 @@ size_t tc_image_bytes(const PropArgs& a);
 int launch_tc_stage_image(const PropArgs& a, unsigned char* image, cudaStream_t st);
 int launch_propagate_tc(const PropArgs& a, cudaStream_t st);
 
+// tensor-core (tcgen05) MLP f and MLP g of every FFBSi candidate (smc_propagate_tc.cu); weight image from
+// launch_tc_stage_image with PropArgs.q1 = the f network
+struct CandTcArgs {
+  const unsigned char* tc_image; const float* sig; const float* obs;
+  const float* mu1i; const float* m2_all; const float* mu_init_all; const float* X_next; const float* eps_bw;
+  float* candF; float* candG;        // (B, N, M) out: f_lp (0 at t = T-1) and g_lp of every candidate
+  unsigned long long seed;
+  int N, M, B, T, Dx, Dy, H, t, seq_offset;
+  unsigned flags;
+};
+bool ffbsi_cand_tc_supported(const psvo_mlp& f, const psvo_mlp& g, int Dx, int Dy, long long rows);
+int launch_ffbsi_cand_tc(const CandTcArgs& a, cudaStream_t st);
+
 // tensor-core (tcgen05) one-hidden-layer MLP over particle rows (tc_mlp.cu)
 bool tc_mlp_supported(const psvo_mlp& net);
 int launch_particle_mlp_tc(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, float* out,

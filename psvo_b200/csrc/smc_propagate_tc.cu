@@ -157,6 +157,36 @@ __device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint64_t a2h, u
   tc::mma_commit(mL2);
 }
 
+// MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1) the
+// chunk schedule  L1(0), L1(1) | L2(c-1), L1(c+1) ...  driven by the group's "operand staged" barrier.
+__device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem& L, uint32_t tmem, uint64_t* bars, int grp, int lane,
+                                            int work, int nchunk, int first_net, const TcNetDesc& nq, const TcNetDesc& ng) {
+  uint64_t* full = bars + 4 * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3;
+  const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
+  const uint64_t a2h = tc::make_desc(tc::smem_u32(sm + L.a2_hi[grp]), 2048, 128), a2l = tc::make_desc(tc::smem_u32(sm + L.a2_lo[grp]), 2048, 128);
+  const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
+  uint32_t phase = 0;
+  for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+    for (int net = first_net; net < 2; ++net) {
+      const TcNetDesc& nd = net ? ng : nq;
+      for (int s2 = 0; s2 <= nchunk; ++s2) {
+        tc::mbar_wait(full, phase); phase ^= 1;
+        tc::fence_after_sync();
+        if (lane == 0) {
+          if (s2 == 0) {
+            tc_issue_l1(nd, a1h, a1l, tD1, 0, mD1);
+            if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, tD1, 1, mD1);
+          } else {
+            tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
+            if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, tD1, s2 + 1, mD1);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // fp16 weight image (layout = the head of TcPropSmem), written once per forward pass
 template <int NPG>
 __global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigned char* __restrict__ img) {
@@ -239,32 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
 
   if (warp >= kTcGroups * 4) {
-    // =================================== MMA-issuing warp of group (warp - 16) ===================================
-    const int grp = warp - kTcGroups * 4;
-    uint64_t* full = bars + 4 * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3;
-    const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
-    const uint64_t a2h = tc::make_desc(tc::smem_u32(sm + L.a2_hi[grp]), 2048, 128), a2l = tc::make_desc(tc::smem_u32(sm + L.a2_lo[grp]), 2048, 128);
-    const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
-    uint32_t phase = 0;
-    for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
-      for (int net = t0 ? 1 : 0; net < 2; ++net) {
-        const TcNetDesc& nd = net ? ng : nq;
-        for (int s2 = 0; s2 <= nchunk; ++s2) {
-          tc::mbar_wait(full, phase); phase ^= 1;
-          tc::fence_after_sync();
-          if (lane == 0) {
-            if (s2 == 0) {
-              tc_issue_l1(nd, a1h, a1l, tD1, 0, mD1);
-              if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, tD1, 1, mD1);
-            } else {
-              tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
-              if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, tD1, s2 + 1, mD1);
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
+    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, t0 ? 1 : 0, nq, ng);
   } else {
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
@@ -387,6 +392,204 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// FFBSi candidates: MLP f and MLP g of every candidate x~[m,i] on tensor cores  (PSVO.py:125,130 -- f.log_prob(bw_X_t,
+// bw_X_tp1) and g.log_prob(bw_X_t, obs[:, t]) on M*N*B rows).  Same pipeline as smc_propagate_tc_kernel (the weight
+// image holds f in the "q" slot); the candidate is recomputed from eps_bw / Philox exactly like ffbsi_step_kernel does.
+// Outputs f_lp and g_lp per candidate, row index (b, i, m).
+// ------------------------------------------------------------------------------------------------------
+template <int NPG>
+__global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N, M = a.M, T = a.T, t = a.t, H = a.H;
+  const bool boot = a.flags & PSVO_F_BOOTSTRAP, poisson = a.flags & PSVO_F_POISSON;
+  const bool last = t == T - 1;
+  const TcPropSmem L = tc_prop_layout(H, NPG);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nchunk = H / kTcChunk;
+
+  float* sb1q = reinterpret_cast<float*>(sm + L.b1q);
+  float* sb2q = reinterpret_cast<float*>(sm + L.b2q);
+  float* sb1g = reinterpret_cast<float*>(sm + L.b1g);
+  float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
+  // consts: sp[16] | inv1[16] | inv2[16] | inv_sf[16] | inv_sg[32] | ld_f ld_g
+  float* C = reinterpret_cast<float*>(sm + L.consts);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    const int n16 = (int)(L.consts / 16);
+#pragma unroll 4
+    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  if (tid < 16) {
+    const int d = tid;
+    const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
+    C[16 + d] = 1.0f / s1; C[32 + d] = 1.0f / s2;
+    C[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
+    C[48 + d] = 1.0f / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+  }
+  if (tid >= 32 && tid < 64) C[64 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
+  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (warp == 0) tc::tmem_alloc(slot, 512);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (tid == 0) {
+    float lf = 0.f, lg = 0.f;
+    for (int d = 0; d < Dx; ++d) lf += logf(a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d]);
+    if (!poisson) for (int d = 0; d < Dy; ++d) lg += logf(a.sig[SIG_G * 32 + d]);
+    C[96] = lf; C[97] = lg;
+  }
+  __syncthreads();
+  const uint32_t tmem = *slot;
+  const long long ncand = (long long)N * M;
+  const int tiles_per_seq = (int)((ncand + 127) / 128);
+  const int work = a.B * tiles_per_seq;
+
+  TcNetDesc nq, ng;
+  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
+  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
+  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
+  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
+
+  if (warp >= kTcGroups * 4) {
+    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, last ? 1 : 0, nq, ng);
+  } else {
+    const int grp = warp >> 2;
+    const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
+    const float* inv_sg = C + 64;
+    const float ld_f = C[96], ld_g = C[97];
+    const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
+    TcGroup g;
+    const int gt = tid & 127;
+    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
+    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
+
+    for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+      const int b = wi / tiles_per_seq;
+      const long long c = (long long)(wi - b * tiles_per_seq) * 128 + gt;
+      const bool live = c < ncand;
+      const int i = live ? (int)(c / M) : 0, m = live ? (int)(c - (long long)i * M) : 0;
+      const size_t bt = (size_t)b * T + t;
+
+      // ---- candidate x~ = mean + sp * eps  (same arithmetic as ffbsi_step_kernel)
+      float x[16];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (4 * cc < Dx) {
+          if (a.eps_bw != nullptr) {
+            const float* src = a.eps_bw + (((bt * M + m) * N + i) * (size_t)Dx);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (4 * cc + k < Dx) e[k] = src[4 * cc + k];
+          } else {
+            const uint64_t gidx = ((((uint64_t)(a.seq_offset + b) * T + t) * M + m) * N) + i;
+            normal4(philox4x32_10(a.seed, gidx, cc, 2u), e);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = 4 * cc + k;
+          float xv = 0.0f;
+          if (d < Dx) {
+            float mean;
+            if (last) mean = a.mu_init_all[bt * Dx + d];
+            else {
+              const float m1 = a.mu1i[((size_t)b * N + i) * Dx + d], m2 = a.m2_all[bt * Dx + d];
+              mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
+            }
+            xv = mean + sp[d] * e[k];
+          }
+          x[d] = xv;
+        }
+      }
+
+      // ---- f(x_{t+1} | x~)
+      float f_lp = 0.0f;
+      if (!last) {
+        tc_mlp_compute(g, x, sb1q, nchunk);
+        float muf[16], mb[16];
+        tc::tmem_ld16(g.tD2, muf);
+        tc::tmem_ld16(g.tD2 + 16, mb);
+        const float* xn = a.X_next + ((bt + 1) * N + i) * Dx;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          if (d < Dx) {
+            const float mu = fmaf(muf[d] + mb[d], kWUnscale, sb2q[d]);
+            const float z = (xn[d] - mu) * inv_sf[d];
+            s = fmaf(z, z, s);
+          }
+        }
+        f_lp = -0.5f * s - ld_f - cx;
+      }
+      // ---- g(y_t | x~)
+      tc_mlp_compute(g, x, sb1g, nchunk);
+      float gsum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < NPG; c0 += 16) {
+        float mug[16], mgb[16];
+        tc::tmem_ld16(g.tD2 + c0, mug);
+        tc::tmem_ld16(g.tD2 + NPG + c0, mgb);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int d = c0 + k;
+          if (d < Dy) {
+            const float y = a.obs[bt * Dy + d];
+            const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
+            const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
+            gsum = fmaf(z, z, gsum);
+          }
+        }
+      }
+      const float g_lp = -0.5f * gsum - ld_g - cy;
+      if (live) {
+        a.candF[(size_t)b * ncand + c] = f_lp;
+        a.candG[(size_t)b * ncand + c] = g_lp;
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+bool ffbsi_cand_tc_supported(const psvo_mlp& f, const psvo_mlp& g, int Dx, int Dy, long long rows) {
+  static const bool disabled = getenv("PSVO_DISABLE_TC") != nullptr && getenv("PSVO_DISABLE_TC")[0] == '1';
+  if (disabled) return false;
+  if (f.n_hidden != 1 || g.n_hidden != 1) return false;
+  const int H = g.width[0];
+  if (f.width[0] != H || H < 128 || H > 256 || (H % 32) != 0) return false;
+  if (Dx > 16 || Dy > 32) return false;
+  return rows >= 128LL * kTcGroups * 32;
+}
+
+int launch_ffbsi_cand_tc(const CandTcArgs& a, cudaStream_t st) {
+  PSVO_REQUIRE(a.tc_image != nullptr, "tensor-core FFBSi candidates: weight image missing");
+  const TcPropSmem L = tc_prop_layout(a.H, 32);
+  const size_t smem = L.total + 128;
+  PSVO_REQUIRE(smem <= 227 * 1024, "tensor-core FFBSi candidates: %zu B of shared memory", smem);
+  const long long tiles = (long long)a.B * (((long long)a.N * a.M + 127) / 128);
+  long long grid = (tiles + kTcGroups - 1) / kTcGroups;
+  if (grid > num_sms()) grid = num_sms();
+  static bool cfg = false;
+  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(ffbsi_cand_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+  ProfScope ps_(PK_FFBSI, st);
+  ffbsi_cand_tc_kernel<32><<<(int)grid, kTcThreads, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
 }
 
 bool tc_propagate_supported(const PropArgs& a) {

@@ -62,6 +62,10 @@ BS_CONFIGS = [
     ("tc_pair_dx16", 16, 32, 16, [64], 256, 8, 1, 3, False, O.Flags()),
     ("tc_pair_wr", 4, 2, 8, [16], 200, 6, 2, 4, True, O.Flags()),
     ("tc_pair_many_tiles", 2, 1, 8, [8], 640, 4, 3, 3, False, O.Flags()),
+    # sizes that also take the tcgen05 candidate-MLP kernel (H >= 128, B*N*M >= 16384)
+    ("tc_cand_h128", 4, 3, 8, [128], 256, 8, 8, 3, False, O.Flags()),
+    ("tc_cand_c5", 16, 32, 16, [256], 520, 4, 8, 3, False, O.Flags()),
+    ("tc_cand_wr_poisson", 3, 2, 8, [160], 300, 7, 8, 3, True, O.Flags(poisson_emission=True)),
 ]
 
 
