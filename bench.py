@@ -42,8 +42,8 @@ WORKLOADS = {
     "c4_allen": dict(cls="AESMC", Dx=4, Dy=1, H=[64], N=2048, T=1000, B=1, poisson=True,
                      note="BASELINE configs[3] shape, poisson emission, N=2048, T=1000, B=1"),
     # FFBSi backward simulation (psvo_ffbsi_forward) measured on its own: value = pair evaluations / s
-    "c5_ffbsi": dict(cls="PSVO", Dx=16, Dy=32, H=[256], N=4096, M=16, T=6, B=8, ffbsi=True, Dfeat=64,
-                     note="FFBSi point of BASELINE configs[4] (N=4096, M=16, Dx=16, Dy=32, H=256); T=6, B=8 slice"),
+    "c5_ffbsi": dict(cls="PSVO", Dx=16, Dy=32, H=[256], N=4096, M=16, T=11, B=16, ffbsi=True, Dfeat=64,
+                     note="FFBSi point of BASELINE configs[4] (N=4096, M=16, Dx=16, Dy=32, H=256); T=11, B=16 slice"),
     "c2_lorenz_psvo": dict(cls="PSVO", Dx=3, Dy=3, H=[32], N=256, M=16, T=500, B=1, ffbsi=True, Dfeat=64,
                            note="BASELINE configs[1] Lorenz shape, PSVO (FFBSi), N=256, M=16, T=500, B=1 (latency-bound)"),
     "tiny": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=512, T=20, B=8, note="smoke-size config-5 shape"),
@@ -217,7 +217,7 @@ def run_ours(args, w, rank, world, local_rank):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
-    logZ_mean = float(bufs["logZ_b"].mean())
+    logZ_mean = float(bufs["logZ_b"].detach().mean())
     if rank != 0:
         return None
 
@@ -387,6 +387,7 @@ def main():
     ap.add_argument("--workload", default="c5_shard", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ffbsi", action="store_true")
     ap.add_argument("--T", type=int, default=None, help="override the number of time steps (debug)")
     ap.add_argument("--B", type=int, default=None, help="override sequences per GPU (debug)")
     args = ap.parse_args()
@@ -416,6 +417,14 @@ def main():
             return
         line = run_ours(args, w, rank, world, local_rank)
         if rank == 0:
+            if world == 1 and not args.no_ffbsi and args.workload == "c5_shard":
+                # the FFBSi point of the same config (BASELINE metric: "SMC+FFBSi"), on a bounded slice
+                wf = dict(WORKLOADS["c5_ffbsi"])
+                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_ffbsi"; fa.steps = 2; fa.warmup = 1
+                fl = run_ffbsi(fa, wf, 0, 1, local_rank)
+                line["ffbsi"] = {"value": fl["value"], "unit": fl["unit"], "ms_per_pass": fl["ms_per_step"],
+                                 "mufu_frac": fl["roofline"]["mufu"]["frac"], "sample": wf["note"],
+                                 "call": "psvo_ffbsi_forward (tcgen05 pairwise term + tcgen05 candidate MLPs)"}
             if world == 1 and not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_sample(w)
             print(json.dumps(line), flush=True)
