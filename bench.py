@@ -224,11 +224,14 @@ def run_ours(args, w, rank, world, local_rank):
     psteps = world * B * T * N
     peaks, peak_src = read_peaks()
     prop_ms_avg = kms[0] / max(kl[0], 1)
+    steps_per_launch = T / max(kl[0], 1)          # 1 for the per-step kernels, T for the persistent whole-filter kernel
     step_ms = ms / args.steps
     flop_ps = flops_per_particle_step(w)
     bytes_ps = 8 * Dx + 4                                             # write X_t, X_anc_t, log_W_t
-    fl_launch = flop_ps * B * N                                       # one propagate launch = one time step of the shard
-    by_launch = (4 * Dx + 4 + 4 * Dx) * B * N                         # propagate itself: read X_anc, write X_t, log_W
+    fl_launch = flop_ps * B * N * steps_per_launch                    # one propagate launch = one time step of the shard
+    by_launch = (4 * Dx + 4 + 4 * Dx) * B * N * steps_per_launch      # propagate itself: read X_anc, write X_t, log_W
+    if kl[0] == 1:
+        by_launch = bytes_ps * B * N * T                              # persistent kernel: the whole pass, all outputs
     hbm_time = bytes_ps * B * N * T / (peaks["hbm_gbs"] * 1e9)
     tensor_time = flop_ps * B * N * T / (peaks["bf16_tflops_sustained"] * 1e12)
     bound = "tensor" if tensor_time > hbm_time else "hbm"
@@ -240,7 +243,7 @@ def run_ours(args, w, rank, world, local_rank):
         achieved = by_launch / (prop_ms_avg * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None}
-    roof.update({"kernel": "smc_propagate_kernel", "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
+    roof.update({"kernel": "smc_filter_persistent_kernel" if kl[0] == 1 else "smc_propagate_kernel", "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
                  "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
                  "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,
                  "kernel_share_of_step": {"smc_propagate": kms[0] / max(sum(kms), 1e-9), "smc_resample": kms[1] / max(sum(kms), 1e-9),

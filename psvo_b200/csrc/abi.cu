@@ -213,6 +213,10 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
   ra.lse = lse; ra.logZ_b = logZ_b; ra.logWbar = w.logWbar; ra.seed = seed;
   ra.N = d->N; ra.B = d->B; ra.T = d->T; ra.Dx = d->Dx; ra.t = 0; ra.seq_offset = d->seq_offset; ra.flags = d->flags; ra.stream_id = 1u;
 
+  {
+    size_t psm = 0; int pblk = 0;
+    if (persistent_filter_supported(pa, plan, &psm, &pblk)) return launch_filter_persistent(pa, ra, plan, st);
+  }
   for (int t = 0; t < d->T; ++t) {
     pa.t = t; ra.t = t;
     if (int e = launch_propagate(pa, plan, st)) return e;

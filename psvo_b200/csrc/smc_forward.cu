@@ -11,6 +11,7 @@
 //   smc_resample  : one CTA per sequence.  log-sum-exp of log_W_t, order-independent fixed-point CDF (integer
 //                   block scan), inverse-CDF binary search per child, ancestor gather X_anc[t] = X_t[a].
 // HBM layout is sequence-major (B,T,N,D): every (b,t) slab a kernel touches is contiguous.
+#include <stdlib.h>
 #include "mlp_tile.cuh"
 #include "smc_kernels.h"
 
@@ -47,26 +48,13 @@ struct StepConsts {        // per-CTA constants in shared memory
   float ld_p, ld_f, ld_g;  // sum log stddev
 };
 
-template <int DXP, int DYP, int PPT>
-__global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int Dx = a.Dx, Dy = a.Dy, N = a.N;
+// per-step constants of one CTA (t = 0 uses q0's stddev as d1, later steps q1's)
+template <int DXP>
+__device__ __forceinline__ void step_consts_init(const PropArgs& a, bool t0, StepConsts<DXP>* C) {
+  const int Dx = a.Dx, Dy = a.Dy;
   const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP;
   const bool poisson = a.flags & PSVO_F_POISSON;
-  const bool t0 = a.t == 0;
-  const bool f_is_d1 = boot && two_q;            // f_lp = d1_mvn.log_prob(X)  (SVO.py:230)
-  const bool sep_f = !boot;                      // a distinct f network exists
-
-  MlpS<DXP, DXP> q1s, fs;
-  MlpS<DXP, DYP> gs;
-  float* p = smem;
-  StepConsts<DXP>* C = reinterpret_cast<StepConsts<DXP>*>(p);
-  p += (sizeof(StepConsts<DXP>) / sizeof(float) + 3) & ~3;
-  if (!t0) p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
-  if (!t0 && sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
-  p = mlp_stage<DXP, DYP>(a.g, p, gs);
-  float* scratch = p;
-
+  const bool f_is_d1 = boot && two_q;
   if (threadIdx.x < DXP) {
     const int d = threadIdx.x;
     const float s1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d];
@@ -85,17 +73,24 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
     C->ld_p = lp; C->ld_f = lf; C->ld_g = lg;
   }
   __syncthreads();
+}
 
-  const int tile = blockDim.x * PPT;
-  const int tiles_per_seq = (N + tile - 1) / tile;
-  const int work = a.B * tiles_per_seq;
+// one tile of blockDim.x * PPT particles of sequence b at time t: propagate + weight  (shared by the per-step kernel
+// and the persistent whole-filter kernel, so both produce the same bits)
+template <int DXP, int DYP, int PPT>
+__device__ __forceinline__ void propagate_tile(const PropArgs& a, const StepConsts<DXP>* C, const MlpS<DXP, DXP>& q1s,
+                                               const MlpS<DXP, DXP>& fs, const MlpS<DXP, DYP>& gs, float* scratch,
+                                               int b, int n0, int t) {
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N;
+  const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP;
+  const bool poisson = a.flags & PSVO_F_POISSON;
+  const bool t0 = t == 0;
+  const bool f_is_d1 = boot && two_q;            // f_lp = d1_mvn.log_prob(X)  (SVO.py:230)
+  const bool sep_f = !boot;                      // a distinct f network exists
   const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
   const float neg_logN = -logf((float)N);
-
-  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
-    const int b = wi / tiles_per_seq;
-    const int n0 = (wi - b * tiles_per_seq) * tile;
-    const size_t bt = (size_t)b * a.T + a.t;
+  {
+    const size_t bt = (size_t)b * a.T + t;
 
     float x[PPT][DXP];        // parent, later the new particle
     float mu1[PPT][DXP];
@@ -160,7 +155,7 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
           for (int d = 0; d < DXP; ++d) e[d] = d < Dx ? src[d] : 0.0f;
         }
       } else {
-        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n_of[pp] : 0);
+        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + (live ? n_of[pp] : 0);
 #pragma unroll
         for (int c = 0; c < DXP / 4; ++c) {
           if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
@@ -219,6 +214,33 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
       if (!t0 && a.logWbar != nullptr && live) lwb = a.logWbar[(size_t)b * N + n_of[pp]];
       if (live) a.log_Ws[bt * N + n_of[pp]] = ((flp[pp] + g_lp) - qlp[pp]) + lwb;
     }
+  }
+}
+
+template <int DXP, int DYP, int PPT>
+__global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N;
+  const bool t0 = a.t == 0;
+  const bool sep_f = !(a.flags & PSVO_F_BOOTSTRAP);
+
+  MlpS<DXP, DXP> q1s, fs;
+  MlpS<DXP, DYP> gs;
+  float* p = smem;
+  StepConsts<DXP>* C = reinterpret_cast<StepConsts<DXP>*>(p);
+  p += (sizeof(StepConsts<DXP>) / sizeof(float) + 3) & ~3;
+  if (!t0) p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
+  if (!t0 && sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
+  p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  float* scratch = p;
+  step_consts_init<DXP>(a, t0, C);
+
+  const int tile = blockDim.x * PPT;
+  const int tiles_per_seq = (N + tile - 1) / tile;
+  const int work = a.B * tiles_per_seq;
+  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const int b = wi / tiles_per_seq;
+    propagate_tile<DXP, DYP, PPT>(a, C, q1s, fs, gs, scratch, b, (wi - b * tiles_per_seq) * tile, a.t);
   }
 }
 
@@ -299,19 +321,18 @@ int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
 // dependent search + gather chains of one sequence spread over several SMs when B alone cannot fill the machine.
 // shared memory: N uint64 (inclusive fixed-point CDF) + N floats (log weights) + chunk ints (ancestors of this part)
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+// normalise + resample + gather for sequence b at time t, children of part `part` of `nparts`; NC: X_t may be read
+// through the non-coherent path (only when a previous kernel wrote it)
+template <bool NC>
+__device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int part, int nparts, int t, unsigned char* smraw,
+                                              unsigned long long* sscr, float* fscr) {
   const int N = a.N, Dx = a.Dx;
   unsigned long long* sC = reinterpret_cast<unsigned long long*>(smraw);
   float* sLW = reinterpret_cast<float*>(sC + N);
   int* sAnc = reinterpret_cast<int*>(sLW + N);
-  __shared__ unsigned long long sscr[33];
-  __shared__ float fscr[33];
-
-  const int b = blockIdx.x, part = blockIdx.y;
-  const int chunk = (N + gridDim.y - 1) / gridDim.y;
+  const int chunk = (N + nparts - 1) / nparts;
   const int n_lo = min(part * chunk, N), n_hi = min(n_lo + chunk, N);
-  const size_t bt = (size_t)b * a.T + a.t;
+  const size_t bt = (size_t)b * a.T + t;
   const float* lw = a.log_Ws + bt * N;
   const int tid = threadIdx.x, nt = blockDim.x;
 
@@ -361,7 +382,7 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
   const float lse = mx + (logf((float)total) - 32.0f * kLn2);
   if (tid == 0 && part == 0) {
     if (a.lse != nullptr) a.lse[bt] = lse;
-    if (a.logZ_b != nullptr) a.logZ_b[b] = (a.t == 0 ? 0.0f : a.logZ_b[b]) + lse;
+    if (a.logZ_b != nullptr) a.logZ_b[b] = (t == 0 ? 0.0f : a.logZ_b[b]) + lse;
   }
 
   const bool resample = a.flags & PSVO_F_RESAMPLE;
@@ -384,7 +405,7 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
           uint32_t u24;
           if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
           else {
-            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + n;
+            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + n;
             u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
           }
           thr[k] = draw_threshold(total, u24);
@@ -428,7 +449,11 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int q = q0 + k * nt;
-        if (q < pieces) { const int c = q / v4, v = q - c * v4; r[k] = __ldg(src4 + (size_t)sAnc[c] * v4 + v); }
+        if (q < pieces) {
+          const int c = q / v4, v = q - c * v4;
+          const float4* sp4 = src4 + (size_t)sAnc[c] * v4 + v;
+          r[k] = NC ? __ldg(sp4) : *sp4;
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -444,6 +469,125 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
       dst[q] = Xt[(size_t)sAnc[c] * Dx + d];
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ unsigned long long sscr[33];
+  __shared__ float fscr[33];
+  resample_body<true>(a, blockIdx.x, blockIdx.y, gridDim.y, a.t, smraw, sscr, fscr);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Persistent whole-filter kernel: ONE launch per forward pass, one CTA per sequence looping over time.
+// For small particle counts / few sequences (BASELINE configs 1-4: B = 1 chains, the reference's own operating
+// point n_particles = 16..64) the two launches per time step are pure latency; here the T dependent steps run
+// back to back with __syncthreads between the propagate and the resample phase.  State goes through the output tensors
+// themselves (L1/L2-resident for one sequence), the arithmetic is the very same device code as the per-step kernels.
+// ------------------------------------------------------------------------------------------------------
+// narrow state / observation dimensions leave enough registers for 1024 threads per CTA (one particle per thread up to
+// N = 1024: the per-step critical path is then a handful of barriers)
+__host__ __device__ constexpr int persist_max_block(int DXP, int DYP) { return (DXP <= 8 && DYP <= 8) ? 1024 : 256; }
+
+template <int DXP, int DYP>
+__global__ void __launch_bounds__(persist_max_block(DXP, DYP), 1) smc_filter_persistent_kernel(PropArgs pa, ResampleArgs ra, int prop_floats) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ unsigned long long sscr[33];
+  __shared__ float fscr[33];
+  const int N = pa.N;
+  const bool sep_f = !(pa.flags & PSVO_F_BOOTSTRAP);
+  MlpS<DXP, DXP> q1s, fs;
+  MlpS<DXP, DYP> gs;
+  float* p = smem;
+  StepConsts<DXP>* C0 = reinterpret_cast<StepConsts<DXP>*>(p);
+  p += (sizeof(StepConsts<DXP>) / sizeof(float) + 3) & ~3;
+  StepConsts<DXP>* C1 = reinterpret_cast<StepConsts<DXP>*>(p);
+  p += (sizeof(StepConsts<DXP>) / sizeof(float) + 3) & ~3;
+  p = mlp_stage<DXP, DXP>(pa.q1, p, q1s);
+  if (sep_f) p = mlp_stage<DXP, DXP>(pa.f, p, fs);
+  p = mlp_stage<DXP, DYP>(pa.g, p, gs);
+  float* scratch = p;
+  unsigned char* rs_smem = reinterpret_cast<unsigned char*>(smem + prop_floats);
+  step_consts_init<DXP>(pa, true, C0);
+  step_consts_init<DXP>(pa, false, C1);
+
+  const int tile = blockDim.x;
+  for (int b = blockIdx.x; b < pa.B; b += gridDim.x) {
+    for (int t = 0; t < pa.T; ++t) {
+      const StepConsts<DXP>* C = t == 0 ? C0 : C1;
+      for (int n0 = 0; n0 < N; n0 += tile) propagate_tile<DXP, DYP, 1>(pa, C, q1s, fs, gs, scratch, b, n0, t);
+      __syncthreads();                     // log_W_t / X_t of this sequence written (block-scope visibility)
+      resample_body<false>(ra, b, 0, 1, t, rs_smem, sscr, fscr);
+      __syncthreads();                     // X_anc_t / logWbar written
+    }
+  }
+}
+
+static bool persistent_env() {
+  static const int v = [] { const char* e = getenv("PSVO_PERSISTENT"); return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1); }();
+  return v != 0;
+}
+
+bool persistent_filter_supported(const PropArgs& a, const PropPlan& pl, size_t* smem_out, int* block_out) {
+  if (!persistent_env()) return false;
+  if (a.tc_image != nullptr && tc_propagate_supported(a)) return false;
+  // one CTA walks a whole sequence: worth it while the per-step launches are latency-bound, i.e. while one step of one
+  // sequence is a small amount of work (measured on B200: config 1 2.1x and config 3 1.5x faster than per-step launches,
+  // config 4 -- N = 2048, H = 64 -- 2x slower, so it stays on the multi-CTA per-step path)
+  if (a.N > 2048 || a.B > 2 * num_sms()) return false;
+  {
+    auto macs = [](const psvo_mlp& net) {
+      long long m = 0; int in = net.d_in;
+      for (int k = 0; k < net.n_hidden; ++k) { m += (long long)in * net.width[k]; in = net.width[k]; }
+      return m + (long long)in * net.d_out;
+    };
+    long long instr = 300 + macs(a.q1) + macs(a.g) + ((a.flags & PSVO_F_BOOTSTRAP) ? 0 : macs(a.f));
+    if ((long long)a.N * instr > 600000) return false;
+  }
+  const int DXP = pad_dx(a.Dx), DYP = pad_dy(a.Dy);
+  int block = ((a.N < 1024 ? a.N : 1024) + 31) & ~31;
+  if (block > persist_max_block(DXP, DYP)) block = persist_max_block(DXP, DYP);
+  // keep every sequence's CTA co-resident (one wave): at 64 registers per thread an SM holds 1024 threads
+  while (block > 128 && (long long)a.B * block > (long long)num_sms() * 1024) block /= 2;
+  if (block < pl.block) block = pl.block < persist_max_block(DXP, DYP) ? pl.block : persist_max_block(DXP, DYP);
+  // propagate region: two StepConsts + all three networks + deep-MLP scratch for `block` threads, one particle each
+  const bool sep_f = !(a.flags & PSVO_F_BOOTSTRAP);
+  auto add = [&](int din_pad, int dout_pad, const psvo_mlp& net) {
+    if (net.n_hidden == 0) return (size_t)(din_pad * dout_pad + dout_pad);
+    size_t n = (size_t)net.width[0] * din_pad + round4(net.width[0]);
+    for (int k = 1; k < net.n_hidden; ++k) n += round4(net.width[k - 1] * net.width[k]) + round4(net.width[k]);
+    return n + (size_t)net.width[net.n_hidden - 1] * dout_pad + dout_pad;
+  };
+  size_t fl = 256 + add(DXP, DXP, a.q1) + (sep_f ? add(DXP, DXP, a.f) : 0) + add(DXP, DYP, a.g);
+  if (pl.scratch_half > 0) fl += 2 * (size_t)(pl.scratch_half / (pl.block * pl.ppt)) * block;
+  fl = (fl + 3) & ~(size_t)3;
+  const size_t total = fl * sizeof(float) + (size_t)a.N * 16;
+  if (total > 100 * 1024) return false;
+  *smem_out = total; *block_out = block;
+  return true;
+}
+
+int launch_filter_persistent(PropArgs pa, const ResampleArgs& ra, const PropPlan& pl, cudaStream_t st) {
+  size_t smem = 0; int block = 0;
+  PSVO_REQUIRE(persistent_filter_supported(pa, pl, &smem, &block), "persistent filter kernel does not support this shape");
+  const int prop_floats = (int)((smem - (size_t)pa.N * 16) / sizeof(float));
+  pa.scratch_half = pl.scratch_half > 0 ? (pl.scratch_half / (pl.block * pl.ppt)) * block : 0;
+  const int DXP = pad_dx(pa.Dx), DYP = pad_dy(pa.Dy);
+  const int grid = pa.B;
+  ProfScope ps_(PK_PROP, st);
+#define PSVO_CASE_P(X, Y)                                                                                           \
+  if (DXP == X && DYP == Y) {                                                                                       \
+    auto kern = smc_filter_persistent_kernel<X, Y>;                                                                 \
+    if (smem > 40 * 1024) PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, block, smem, st>>>(pa, ra, prop_floats);                                                           \
+    PSVO_LAUNCH_CHECK();                                                                                            \
+    return 0;                                                                                                       \
+  }
+  PSVO_CASE_P(4, 4) PSVO_CASE_P(4, 8) PSVO_CASE_P(4, 16) PSVO_CASE_P(4, 32)
+  PSVO_CASE_P(8, 4) PSVO_CASE_P(8, 8) PSVO_CASE_P(8, 16) PSVO_CASE_P(8, 32)
+  PSVO_CASE_P(16, 4) PSVO_CASE_P(16, 8) PSVO_CASE_P(16, 16) PSVO_CASE_P(16, 32)
+#undef PSVO_CASE_P
+  return fail("unsupported padded dims Dx=%d Dy=%d", pa.Dx, pa.Dy);
 }
 
 int launch_resample(const ResampleArgs& a, cudaStream_t st) {

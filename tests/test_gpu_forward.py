@@ -253,3 +253,18 @@ def test_kalman_known_answer_on_gpu():
     # a bootstrap filter's log-likelihood estimate has O(sqrt(T/N)) noise per sequence (T=25, Dy=4, sharp emission)
     assert np.abs(got - np.array(kls)).max() < 1.5, (got, kls)
     assert abs(got.mean() - np.mean(kls)) < 0.3
+
+
+def test_per_step_kernels_when_persistent_path_is_disabled():
+    """Small shapes take the persistent whole-filter kernel; re-run the filter parity tests in a subprocess with
+    PSVO_PERSISTENT=0 so the per-step propagate / resample kernels keep their coverage at the same shapes."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("PSVO_PERSISTENT") == "0":
+        pytest.skip("already inside the per-step re-run")
+    env = dict(os.environ, PSVO_PERSISTENT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x",
+                        "-k", "forward_filter or philox_mode or sharded or kalman"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
