@@ -46,8 +46,22 @@ WORKLOADS = {
                      note="FFBSi point of BASELINE configs[4] (N=4096, M=16, Dx=16, Dy=32, H=256); T=11, B=16 slice"),
     "c2_lorenz_psvo": dict(cls="PSVO", Dx=3, Dy=3, H=[32], N=256, M=16, T=500, B=1, ffbsi=True, Dfeat=64,
                            note="BASELINE configs[1] Lorenz shape, PSVO (FFBSi), N=256, M=16, T=500, B=1 (latency-bound)"),
+    # one training epoch of the reference's notebook run (notebooks/PSVO.ipynb: PSVO, FHN, N=16, T=200, batch 1, 200 sequences):
+    # forward filter + FFBSi + reverse mode + Adam per sequence, through psvo_b200.trainer-style calls
+    "c1_psvo_train": dict(cls="PSVO", Dx=2, Dy=1, H=[32], N=16, M=16, T=200, B=1, train=True, n_seq=200,
+                          note="notebooks/PSVO.ipynb training run shape: PSVO, Dx=2, Dy=1, N=16, M=16, T=200, batch 1, 200 sequences/epoch"),
     "tiny": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=512, T=20, B=8, note="smoke-size config-5 shape"),
 }
+
+
+def read_traffic(workload):
+    """measured DRAM bytes per launch of the dominant kernel (profiles/traffic.json, from ncu --set full), or None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(workload, {}).get("bytes_per_launch")
+    except Exception:
+        return None
 
 
 def read_peaks():
@@ -243,6 +257,8 @@ def run_ours(args, w, rank, world, local_rank):
         achieved = by_launch / (prop_ms_avg * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+    if args.T is None and args.B is None:
+        roof["traffic"] = read_traffic(args.workload)
     roof.update({"kernel": "smc_filter_persistent_kernel" if kl[0] == 1 else "smc_propagate_kernel", "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
                  "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
                  "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,
@@ -326,6 +342,52 @@ def run_ffbsi(args, w, rank, world, local_rank):
                                   "note": "1 ex2 per pair; 148 SMs x 16/clk x 1.965 GHz"},
                          "ffbsi_ms_per_pass": kms[5], "ffbsi_launches": int(kl[5])},
             "log_ZSMC": float(r["logZ_b"].mean())}
+
+
+def run_train_epoch(args, w, local_rank):
+    """seconds per training epoch (forward + reverse + Adam, batch 1) next to the notebook's recorded 93-123 s."""
+    from psvo_b200.flags import default_flags
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.PSVO import PSVO
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    F = default_flags(Dx=w["Dx"], Dy=w["Dy"], n_particles=w["N"], n_particles_for_BSim_proposal=w["M"], time=w["T"],
+                      batch_size=w["B"], PSVO=True)
+    model = SSM(F)
+    smc = PSVO(model, F)
+    obs = synth_obs(w, w["n_seq"], 7, 0).to(dev)
+    with torch.no_grad():
+        smc.get_log_ZSMC(obs[:1].contiguous(), None)            # lazy build
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+
+    def epoch():
+        last = None
+        for j in range(0, w["n_seq"], w["B"]):
+            opt.zero_grad(set_to_none=True)
+            log_ZSMC, _ = smc.get_log_ZSMC(obs[j:j + w["B"]].contiguous(), None)
+            (-log_ZSMC).backward()
+            opt.step()
+            last = log_ZSMC
+        return float(last.detach())
+    first = epoch()                                             # warm-up epoch (also the first of the training curve)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        lastv = epoch()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    psteps = w["n_seq"] * w["T"] * w["N"]
+    return {"metric": "seconds per training epoch (PSVO objective: filter + FFBSi + reverse mode + Adam, batch 1)",
+            "value": sec, "unit": "s/epoch", "n_gpus": 1, "steps": len(times), "warmup": 1, "ms_per_step": sec * 1e3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": sec / 102.0, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": w["note"]},
+            "training_particle_steps_per_s": psteps / sec,
+            "published_reference": "TF 1.12 CPU: 93-123 s/epoch, ~102 s steady (notebooks/PSVO.ipynb:594-602,1704-1708; "
+                                   "different machine, M=8 there) = ~6.3k particle-steps/s",
+            "log_ZSMC_first_last": [first, lastv]}
 
 
 def cpu_sample(w, budget_s=15.0, threads=None):
@@ -413,6 +475,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if w.get("train"):
+            print(json.dumps(run_train_epoch(args, w, local_rank)), flush=True)
+            return
         if w.get("ffbsi"):
             line = run_ffbsi(args, w, rank, world, local_rank)
             if rank == 0:

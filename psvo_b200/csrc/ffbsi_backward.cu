@@ -26,6 +26,8 @@
 //                    sequence, accumulate d/d mu_f[j] and d/d log Wbar[j]; MLP f reverse -> g_Xs[t-1], dW_f.
 //   ffbsi_bwd_traj : (t <= T-2) thread per trajectory: MLP q1_inv reverse -> gradient w.r.t. x_{t+1}^{bw}, handed
 //                    to the picked candidate of step t+1 (through PSVOwR's second gather when present).
+#include <map>
+#include <mutex>
 #include "mlp_bwd_tile.cuh"
 #include "smc_kernels.h"
 
@@ -608,7 +610,17 @@ static size_t staged_fl(const psvo_mlp& net, int din_pad, int dout_pad) {
 
 template <typename K>
 static int launch_fb(K kern, const FbArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-  if (smem > 40 * 1024) PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) {
+    // raise the dynamic shared-memory limit once per kernel (a driver call per launch would dominate small steps)
+    static std::mutex mu;
+    static std::map<const void*, size_t> configured;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = configured[reinterpret_cast<const void*>(kern)];
+    if (smem > have) {
+      PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      have = smem;
+    }
+  }
   ProfScope ps_(PK_FFBSI, st);
   kern<<<grid, block, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
