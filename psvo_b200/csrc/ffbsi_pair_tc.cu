@@ -29,18 +29,24 @@
 
 namespace psvo {
 
-constexpr int kPtStages = 4;
-constexpr int kPtTileBytes = 12288;      // 128 columns: hi+ext K=32 (4 K-groups x 2 KB) | lo K=16 (2 K-groups x 2 KB)
-constexpr int kPtThreads = 2 * 128 + 64;
+constexpr int kPtGroups = 4;             // compute groups (128 candidate rows each) per CTA: 16 warps keep the MUFU pipe fed
+constexpr int kPtCols = 64;              // columns (filter particles j) per tile = accumulator width; 4 groups x 2 buffers x 64 = 512 TMEM columns
+constexpr int kPtStages = 6;
+constexpr int kPtKg = kPtCols * 16;      // bytes of one K-group (8 k) of a B tile
+constexpr int kPtTileBytes = 6 * kPtKg;  // hi+ext K=32 (4 K-groups) | lo K=16 (2 K-groups)
+constexpr int kPtABytes = 12288;         // A operand of one group: 128 rows, same K-group structure (2 KB per K-group)
+constexpr int kPtThreads = kPtGroups * 128 + 96;   // + 2 MMA warps (groups 0-1, 2-3) + 1 TMA producer warp
 constexpr float kPtScale = 16.0f;        // operand scale (exact); the accumulator holds 256 * (dot + c_j)
 constexpr float kPtSentinel = -60000.0f; // c_j of padded columns / zero-weight particles (finite in fp16)
 
 // ---- B image: per (sequence, 128-column tile) the UMMA B operand [N = 128 rows j][K] ----------------------------
 __global__ void __launch_bounds__(128) ffbsi_pair_prep_kernel(PairTcArgs a) {
-  const int ct = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
-  const int N = a.N, Dx = a.Dx, NT = (N + 127) / 128;
+  const int b = blockIdx.y;
+  const int N = a.N, Dx = a.Dx, NT = (N + kPtCols - 1) / kPtCols;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP;
-  const int j = ct * 128 + r;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int ct = j / kPtCols, r = j - ct * kPtCols;
+  if (ct >= NT) return;
   const bool live = j < N;
   const size_t btm = (size_t)b * a.T + (a.t - 1);
   float mus[16];
@@ -62,14 +68,14 @@ __global__ void __launch_bounds__(128) ffbsi_pair_prep_kernel(PairTcArgs a) {
     for (int i = 0; i < 8; ++i) v[i] = mus[kg * 8 + i] * kPtScale;
     uint4 hi, lo;
     tc::split8_f16(v, hi, lo);
-    *reinterpret_cast<uint4*>(img + kg * 2048 + r * 16) = hi;
-    *reinterpret_cast<uint4*>(img + 8192 + kg * 2048 + r * 16) = lo;
+    *reinterpret_cast<uint4*>(img + kg * kPtKg + r * 16) = hi;
+    *reinterpret_cast<uint4*>(img + 4 * kPtKg + kg * kPtKg + r * 16) = lo;
   }
   const __half ch = __float2half_rn(cj);
   const __half cl = __float2half_rn(cj - __half2float(ch));
   const __half2 c2 = __halves2half2(ch, cl);
-  *reinterpret_cast<uint4*>(img + 2 * 2048 + r * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&c2), 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(img + 3 * 2048 + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(img + 2 * kPtKg + r * 16) = make_uint4(*reinterpret_cast<const uint32_t*>(&c2), 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(img + 3 * kPtKg + r * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // one MUFU instruction: 2^x, flush-to-zero (arguments are <= 0 here; relative error ~2^-22)
@@ -79,11 +85,29 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (x <= 0): round-to-nearest split x = n + f, |f| <= 1/2, degree-6 Taylor of 2^f (relative error
+// 1.2e-7), exponent patched with integer arithmetic.  One pair in four goes this way so that the MUFU pipe -- the bound of
+// this kernel -- and the FMA pipe work side by side (the trick of FlashAttention-4's software exp).
+__device__ __forceinline__ float poly_ex2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float n = t - 12582912.0f;
+  const float f = x - n;
+  float p = 1.5403530e-4f;
+  p = fmaf(p, f, 1.3333558e-3f);
+  p = fmaf(p, f, 9.6181291e-3f);
+  p = fmaf(p, f, 5.5504109e-2f);
+  p = fmaf(p, f, 2.4022651e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 struct PtSmem { uint32_t stage, aop, bars, slot, consts, total; };
 __host__ __device__ inline PtSmem pt_layout() {
   PtSmem s; uint32_t o = 0;
   s.stage = o; o += kPtStages * kPtTileBytes;
-  s.aop = o; o += 2 * kPtTileBytes;
+  s.aop = o; o += kPtGroups * kPtABytes;
   s.bars = o; o += 256;
   s.slot = o; o += 128;
   s.consts = o; o += 4 * 16 * 4;
@@ -99,18 +123,18 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
   const bool last = t == T - 1;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int NT = (N + 127) / 128;
+  const int NT = (N + kPtCols - 1) / kPtCols;
   const long long ncand = (long long)N * M;
   const int rt_per_seq = (int)((ncand + 127) / 128);
-  const int items_per_seq = (rt_per_seq + 1) / 2;
+  const int items_per_seq = (rt_per_seq + kPtGroups - 1) / kPtGroups;
   const int work = a.B * items_per_seq;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-  uint64_t* full = bars;                    // [S]   B stage loaded        (1 arrival + tx bytes)
-  uint64_t* empty = bars + kPtStages;       // [S]   B stage consumed      (tcgen05.commit)
-  uint64_t* dfull = bars + 2 * kPtStages;   // [g*2+buf] accumulator ready (tcgen05.commit)
-  uint64_t* dempty = dfull + 4;             // [g*2+buf] accumulator read  (128 arrivals)
-  uint64_t* afull = dempty + 4;             // [g]   A operand staged      (128 arrivals)
+  uint64_t* full = bars;                          // [S]   B stage loaded        (1 arrival + tx bytes)
+  uint64_t* empty = bars + kPtStages;             // [S]   B stage consumed      (one tcgen05.commit per MMA warp)
+  uint64_t* dfull = bars + 2 * kPtStages;         // [g*2+buf] accumulator ready (tcgen05.commit)
+  uint64_t* dempty = dfull + 2 * kPtGroups;       // [g*2+buf] accumulator read  (128 arrivals)
+  uint64_t* afull = dempty + 2 * kPtGroups;       // [g]   A operand staged      (128 arrivals)
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
   float* C = reinterpret_cast<float*>(sm + L.consts);   // sp[16] | inv1[16] | inv2[16] | sf[16]
 
@@ -122,9 +146,9 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
     C[48 + d] = a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
   }
   if (tid == 32) {
-    for (int s = 0; s < kPtStages; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-    for (int k = 0; k < 4; ++k) { tc::mbar_init(dfull + k, 1); tc::mbar_init(dempty + k, 128); }
-    tc::mbar_init(afull, 128); tc::mbar_init(afull + 1, 128);
+    for (int s = 0; s < kPtStages; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 2); }
+    for (int k = 0; k < 2 * kPtGroups; ++k) { tc::mbar_init(dfull + k, 1); tc::mbar_init(dempty + k, 128); }
+    for (int k = 0; k < kPtGroups; ++k) tc::mbar_init(afull + k, 128);
   }
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
@@ -133,7 +157,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
   tc::fence_after_sync();
   const uint32_t tmem = *slot;
 
-  if (warp == 9) {
+  if (warp == kPtGroups * 4 + 2) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t q = 0;
@@ -149,36 +173,38 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ================================ MMA issuer ================================
+  } else if (warp >= kPtGroups * 4) {
+    // ================================ MMA issuers: warp 16 serves groups 0-1, warp 17 groups 2-3 ================================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(128, 128);
+      const int g0 = (warp - kPtGroups * 4) * 2;
+      const uint32_t idesc = tc::make_idesc_f16(128, kPtCols);
       uint64_t adesc_hi[2], adesc_lo[2];
-      for (int g = 0; g < 2; ++g) {
-        adesc_hi[g] = tc::make_desc(tc::smem_u32(sm + L.aop + g * kPtTileBytes), 2048, 128);
-        adesc_lo[g] = tc::make_desc(tc::smem_u32(sm + L.aop + g * kPtTileBytes + 8192), 2048, 128);
+      for (int k = 0; k < 2; ++k) {
+        adesc_hi[k] = tc::make_desc(tc::smem_u32(sm + L.aop + (g0 + k) * kPtABytes), 2048, 128);
+        adesc_lo[k] = tc::make_desc(tc::smem_u32(sm + L.aop + (g0 + k) * kPtABytes + 8192), 2048, 128);
       }
       uint32_t q = 0, it = 0;
       for (int wi = blockIdx.x; wi < work; wi += gridDim.x, ++it) {
-        tc::mbar_wait(afull, it & 1u);
-        tc::mbar_wait(afull + 1, it & 1u);
+        tc::mbar_wait(afull + g0, it & 1u);
+        tc::mbar_wait(afull + g0 + 1, it & 1u);
         tc::fence_after_sync();
         for (int ct = 0; ct < NT; ++ct, ++q) {
           const uint32_t s = q % kPtStages;
           tc::mbar_wait(full + s, (q / kPtStages) & 1u);
           tc::fence_after_sync();
-          const uint64_t bhi = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes), 2048, 128);
-          const uint64_t blo = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes + 8192), 2048, 128);
+          const uint64_t bhi = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes), kPtKg, 128);
+          const uint64_t blo = tc::make_desc(tc::smem_u32(sm + L.stage + s * kPtTileBytes + 4 * kPtKg), kPtKg, 128);
           const uint32_t buf = q & 1u;
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int k = 0; k < 2; ++k) {
+            const int g = g0 + k;
             tc::mbar_wait(dempty + g * 2 + buf, ((q >> 1) & 1u) ^ 1u);
             tc::fence_after_sync();
-            const uint32_t d = tmem + (uint32_t)(g * 2 + buf) * 128u;
-            tc::mma_bf16(d, adesc_hi[g], bhi, idesc, false);                          // hi * hi
-            tc::mma_bf16(d, adesc_hi[g] + (4096 >> 4), bhi + (4096 >> 4), idesc, true);   // 256 * (c_hi + c_lo)
-            tc::mma_bf16(d, adesc_hi[g], blo, idesc, true);                           // hi * lo
-            tc::mma_bf16(d, adesc_lo[g], bhi, idesc, true);                           // lo * hi
+            const uint32_t d = tmem + (uint32_t)(g * 2 + buf) * (uint32_t)kPtCols;
+            tc::mma_bf16(d, adesc_hi[k], bhi, idesc, false);                                          // hi * hi
+            tc::mma_bf16(d, adesc_hi[k] + (4096 >> 4), bhi + ((2 * kPtKg) >> 4), idesc, true);          // 256 * (c_hi + c_lo)
+            tc::mma_bf16(d, adesc_hi[k], blo, idesc, true);                                           // hi * lo
+            tc::mma_bf16(d, adesc_lo[k], bhi, idesc, true);                                           // lo * hi
             tc::mma_commit(dfull + g * 2 + buf);
           }
           tc::mma_commit(empty + s);
@@ -191,13 +217,13 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
     const int g = warp >> 2;
     const int gt = tid & 127;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* sf = C + 48;
-    unsigned char* pa = sm + L.aop + g * kPtTileBytes + gt * 16;
+    unsigned char* pa = sm + L.aop + g * kPtABytes + gt * 16;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float kexp = 1.4426950408889634f / (kPtScale * kPtScale);
     uint32_t q = 0;
     for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
       const int b = wi / items_per_seq;
-      const int rt = (wi - b * items_per_seq) * 2 + g;
+      const int rt = (wi - b * items_per_seq) * kPtGroups + g;
       const long long c = (long long)rt * 128 + gt;
       const bool live = rt < rt_per_seq && c < ncand;
       const int i = live ? (int)(c / M) : 0, m = live ? (int)(c - (long long)i * M) : 0;
@@ -257,29 +283,40 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
       tc::fence_before_sync();
       tc::mbar_arrive(afull + g);
 
-      // ---- online log-sum-exp over the column tiles (accumulator units: 256 * natural log)
+      // ---- online log-sum-exp over the column tiles (accumulator units: 256 * natural log).  The TMEM read of the next
+      //      32 columns is in flight while the current 32 are folded in (two register buffers); the accumulator is
+      //      handed back to the MMA warp as soon as its last columns are in registers.
       float mD = -INFINITY, sum = 0.0f;
+      auto fold = [&](const uint32_t (&r)[32]) {
+        float cm = __uint_as_float(r[0]);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) cm = fmaxf(cm, __uint_as_float(r[k]));
+        if (cm > mD) { sum *= fast_ex2((mD - cm) * kexp); mD = cm; }
+        const float off = -mD * kexp;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          s0 += fast_ex2(fmaf(__uint_as_float(r[k]), kexp, off));
+          s1 += fast_ex2(fmaf(__uint_as_float(r[k + 1]), kexp, off));
+          s2 += fast_ex2(fmaf(__uint_as_float(r[k + 2]), kexp, off));
+          s3 += poly_ex2(fmaf(__uint_as_float(r[k + 3]), kexp, off));
+        }
+        sum += (s0 + s1) + (s2 + s3);
+      };
+      uint32_t va[32], vb[32];
       for (int ct = 0; ct < NT; ++ct, ++q) {
         const uint32_t buf = q & 1u;
         tc::mbar_wait(dfull + g * 2 + buf, (q >> 1) & 1u);
         tc::fence_after_sync();
-        const uint32_t td = tmem + (uint32_t)(g * 2 + buf) * 128u + lane_base;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          float v[32];
-          tc::tmem_ld32(td + cc * 32, v);
-          float cm = v[0];
-#pragma unroll
-          for (int k = 1; k < 32; ++k) cm = fmaxf(cm, v[k]);
-          if (cm > mD) { sum *= fast_ex2((mD - cm) * kexp); mD = cm; }
-          const float off = -mD * kexp;
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) { s0 += fast_ex2(fmaf(v[k], kexp, off)); s1 += fast_ex2(fmaf(v[k + 1], kexp, off)); }
-          sum += s0 + s1;
-        }
+        const uint32_t td = tmem + (uint32_t)(g * 2 + buf) * (uint32_t)kPtCols + lane_base;
+        tc::tmem_ld32_issue(td, va);
+        tc::tmem_ld32_issue(td + 32, vb);
+        tc::tmem_ld32_wait(va);
+        tc::tmem_ld32_wait(vb);
         tc::fence_before_sync();
-        tc::mbar_arrive(dempty + g * 2 + buf);
+        tc::mbar_arrive(dempty + g * 2 + buf);        // all 64 columns are in registers: the MMA warp may overwrite them
+        fold(va);
+        fold(vb);
       }
       if (live) a.candP[(size_t)b * ncand + c] = (mD * (1.0f / (kPtScale * kPtScale)) + logf(sum)) + rr;
     }
@@ -297,13 +334,12 @@ bool ffbsi_pair_tc_supported(int N, int M, int B, int Dx) {
   return N >= 128 && (long long)B * N * M >= 2048;
 }
 
-size_t ffbsi_pair_tc_image_bytes(int B, int N) { return (size_t)B * ((N + 127) / 128) * kPtTileBytes; }
+size_t ffbsi_pair_tc_image_bytes(int B, int N) { return (size_t)B * ((N + kPtCols - 1) / kPtCols) * kPtTileBytes; }
 
 int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
-  const int NT = (a.N + 127) / 128;
   {
     ProfScope ps_(PK_FFBSI, st);
-    ffbsi_pair_prep_kernel<<<dim3(NT, a.B), 128, 0, st>>>(a);
+    ffbsi_pair_prep_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a);
     PSVO_LAUNCH_CHECK();
   }
   const PtSmem L = pt_layout();
@@ -311,7 +347,7 @@ int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(ffbsi_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
   const long long ncand = (long long)a.N * a.M;
-  const long long work = (long long)a.B * (((ncand + 127) / 128 + 1) / 2);
+  const long long work = (long long)a.B * (((ncand + 127) / 128 + kPtGroups - 1) / kPtGroups);
   const int grid = (int)(work < num_sms() ? work : num_sms());
   ProfScope ps_(PK_FFBSI, st);
   ffbsi_pair_tc_kernel<<<grid, kPtThreads, smem, st>>>(a);
