@@ -461,9 +461,14 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   if (int e = pick_block(64 + 2 * staged_floats(a.g, DXP, DYP), DXP, DYP, &blkE, &smE)) return e;
   const size_t fixedP = 5 * DXP + 256 + 2 * staged_floats(a.q1, DXP, DXP) + (sep_f ? 2 * staged_floats(a.f, DXP, DXP) : 0);
   if (int e = pick_block(fixedP, DXP, DXP, &blkP, &smP)) return e;
-  auto grid_of = [&](int block) {
+  // persistent CTAs: as many per SM as shared memory and the thread budget allow (each CTA flushes its gradient
+  // accumulator once, so more than a few per SM only adds atomics)
+  auto grid_of = [&](int block, size_t smem) {
     const int64_t work = (int64_t)B * ((N + block - 1) / block);
-    const int64_t cap = num_sms();
+    int per_sm = (int)((220 * 1024) / (smem > 0 ? smem : 1));
+    if (per_sm > 2048 / block) per_sm = 2048 / block;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    const int64_t cap = (int64_t)num_sms() * per_sm;
     return (int)(work < cap ? work : cap);
   };
 
@@ -473,15 +478,15 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
     a.t = t; a.gXin = gXin; a.gXout = gXout;
     if (t > 0) PSVO_CUDA(cudaMemsetAsync(gXout, 0, BN * Dx * sizeof(float), st));
     int rc = -1;
-#define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, grid_of(blkE), smE, st);
+#define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, grid_of(blkE, smE), smE, st);
     PSVO_CASE_E(4, 4) PSVO_CASE_E(4, 8) PSVO_CASE_E(4, 16) PSVO_CASE_E(4, 32)
     PSVO_CASE_E(8, 4) PSVO_CASE_E(8, 8) PSVO_CASE_E(8, 16) PSVO_CASE_E(8, 32)
     PSVO_CASE_E(16, 4) PSVO_CASE_E(16, 8) PSVO_CASE_E(16, 16) PSVO_CASE_E(16, 32)
 #undef PSVO_CASE_E
     if (rc) return rc;
-    rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP), smP, st)
-                  : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP), smP, st)
-                              : launch_proposal_t<16>(a, blkP, grid_of(blkP), smP, st));
+    rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP, smP), smP, st)
+                  : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
+                              : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
     if (rc) return rc;
     float* tmp = gXin; gXin = gXout; gXout = tmp;
   }
