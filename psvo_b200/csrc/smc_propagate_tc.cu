@@ -33,10 +33,14 @@ namespace psvo {
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
-constexpr float kWScale = 256.0f, kWUnscale = 1.0f / 256.0f;
+// exact power-of-two operand scales: W1 (and its bias) by 2^4, W2 by 2^8 -> their fp16 lo halves stay normal; the hidden
+// activations travel in 16x units (|h| < 4094) and the layer-2 accumulator in 4096x units, undone in the output FFMA
+constexpr float kW1Scale = 16.0f, kW2Scale = 256.0f, kWUnscale = 1.0f / (16.0f * 256.0f);
 
 struct TcPropSmem {
   uint32_t w1q_hi, w1q_lo, w2q, w1g_hi, w1g_lo, w2g;   // fp16 weights (B operands); w2*: [K-group][hi rows | lo rows]
+  uint32_t w1q_b, w1g_b;                               // layer-1 bias as a B operand [H x K=16]: k=0 b_hi, k=1 b_lo
+  uint32_t a_ones;                                     // its A operand [128 x K=16]: k=0,1 = 1 (same for every row)
   uint32_t b1q, b2q, b1g, b2g, consts;                                        // fp32
   uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups], a2_hi[kTcGroups], a2_lo[kTcGroups];
   uint32_t bars, slot, total;
@@ -50,19 +54,21 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   s.w2q = PSVO_TAKE(2 * 16 * H * 2);
   s.w1g_hi = PSVO_TAKE(H * 16 * 2); s.w1g_lo = PSVO_TAKE(H * 16 * 2);
   s.w2g = PSVO_TAKE(2 * NPG * H * 2);
+  s.w1q_b = PSVO_TAKE(H * 16 * 2); s.w1g_b = PSVO_TAKE(H * 16 * 2);
   s.b1q = PSVO_TAKE(H * 4); s.b2q = PSVO_TAKE(16 * 4); s.b1g = PSVO_TAKE(H * 4); s.b2g = PSVO_TAKE(32 * 4);
   s.consts = PSVO_TAKE(160 * 4);
   for (int g = 0; g < kTcGroups; ++g) {
     s.a1_hi[g] = PSVO_TAKE(128 * 16 * 2); s.a1_lo[g] = PSVO_TAKE(128 * 16 * 2);
     s.a2_hi[g] = PSVO_TAKE(128 * kTcChunk * 2); s.a2_lo[g] = PSVO_TAKE(128 * kTcChunk * 2);
   }
+  s.a_ones = PSVO_TAKE(128 * 16 * 2);
   s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full, mD1[0], mD1[1], mL2
 #undef PSVO_TAKE
   s.total = o;
   return s;
 }
 
-struct TcNetDesc { uint64_t w1h, w1l, w2; uint32_t idesc2a, idesc2b; int NP; };
+struct TcNetDesc { uint64_t w1h, w1l, w1b, w2; uint32_t idesc2a, idesc2b; int NP; };
 
 struct TcGroup {
   unsigned char *pa2h, *pa2l;      // this thread's 16-byte slot in the A2 operand (K-group 0)
@@ -82,22 +88,17 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
 
 // hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> scale + bias -> ReLU -> fp16 hi/lo -> A2 -> arrive
 template <int BUF>
-__device__ __forceinline__ void tc_chunk(TcGroup& g, const float* __restrict__ sb1, int c) {
+__device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
   tc_wait<BUF>(g.mD1 + BUF, g.par);                                       // L1(c) complete
   tc::fence_after_sync();
   float v[32];
   tc::tmem_ld32(g.tD1 + BUF * 32, v);
   uint4 hi[4], lo[4];
-  const float* bias = sb1 + c * kTcChunk;
 #pragma unroll
   for (int kg = 0; kg < 4; ++kg) {
     float h[8];
-    const float4 ba = *reinterpret_cast<const float4*>(bias + kg * 8);
-    const float4 bb = *reinterpret_cast<const float4*>(bias + kg * 8 + 4);
-    h[0] = fmaxf(fmaf(v[kg * 8 + 0], kWUnscale, ba.x), 0.f); h[1] = fmaxf(fmaf(v[kg * 8 + 1], kWUnscale, ba.y), 0.f);
-    h[2] = fmaxf(fmaf(v[kg * 8 + 2], kWUnscale, ba.z), 0.f); h[3] = fmaxf(fmaf(v[kg * 8 + 3], kWUnscale, ba.w), 0.f);
-    h[4] = fmaxf(fmaf(v[kg * 8 + 4], kWUnscale, bb.x), 0.f); h[5] = fmaxf(fmaf(v[kg * 8 + 5], kWUnscale, bb.y), 0.f);
-    h[6] = fmaxf(fmaf(v[kg * 8 + 6], kWUnscale, bb.z), 0.f); h[7] = fmaxf(fmaf(v[kg * 8 + 7], kWUnscale, bb.w), 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = fmaxf(v[kg * 8 + i], 0.f);          // D1 = 16 (W1^T x + b1): the bias rode in the MMA
     tc::split8_f16_trunc(h, hi[kg], lo[kg]);
   }
   if (c > 0) tc_wait<2>(g.mL2, g.par);                                     // L2(c-1) complete -> A2 reusable
@@ -112,8 +113,8 @@ __device__ __forceinline__ void tc_chunk(TcGroup& g, const float* __restrict__ s
 }
 
 // compute-group side of one network: x = this thread's input row.  On return the accumulator D2 (2*NP columns:
-// [hi*hi + lo*hi | hi*lo]) is complete; (D2[:, :NP] + D2[:, NP:]) / kWScale = W2^T relu(W1^T x + b1).
-__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], const float* __restrict__ sb1, int nchunk) {
+// [hi*hi + lo*hi | hi*lo]) is complete; (D2[:, :NP] + D2[:, NP:]) * kWUnscale = W2^T relu(W1^T x + b1).
+__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], int nchunk) {
 #pragma unroll
   for (int kg = 0; kg < 2; ++kg) {
     float v[8];
@@ -128,21 +129,23 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16],
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
   tc::mbar_arrive(g.full);
   for (int c = 0; c < nchunk; c += 2) {
-    tc_chunk<0>(g, sb1, c);
-    if (c + 1 < nchunk) tc_chunk<1>(g, sb1, c + 1);
+    tc_chunk<0>(g, c);
+    if (c + 1 < nchunk) tc_chunk<1>(g, c + 1);
   }
   tc_wait<2>(g.mL2, g.par);                                                // L2(last) complete
   tc::fence_after_sync();
 }
 
 // MMA-warp side (one elected lane): L1(c) -> D1[c & 1]
-__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint32_t tD1, int c, uint64_t* mD1) {
+__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t aones, uint32_t tD1, int c,
+                                            uint64_t* mD1) {
   const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
   const uint32_t d = tD1 + (c & 1) * 32;
-  const uint64_t bh = nd.w1h + (uint64_t)(c * (kTcChunk * 16 / 16)), bl = nd.w1l + (uint64_t)(c * (kTcChunk * 16 / 16));
-  tc::mma_bf16(d, a1h, bh, idesc1, false);
-  tc::mma_bf16(d, a1h, bl, idesc1, true);
-  tc::mma_bf16(d, a1l, bh, idesc1, true);
+  const uint64_t off = (uint64_t)(c * (kTcChunk * 16 / 16));
+  tc::mma_bf16(d, a1h, nd.w1h + off, idesc1, false);
+  tc::mma_bf16(d, a1h, nd.w1l + off, idesc1, true);
+  tc::mma_bf16(d, a1l, nd.w1h + off, idesc1, true);
+  tc::mma_bf16(d, aones, nd.w1b + off, idesc1, true);                      // + 16 b1 (hi + lo)
   tc::mma_commit(mD1 + (c & 1));
 }
 // L2(c): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)  and  a_lo x w_hi (N = NP)
@@ -164,6 +167,7 @@ __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem&
   uint64_t* full = bars + 4 * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3;
   const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
   const uint64_t a2h = tc::make_desc(tc::smem_u32(sm + L.a2_hi[grp]), 2048, 128), a2l = tc::make_desc(tc::smem_u32(sm + L.a2_lo[grp]), 2048, 128);
+  const uint64_t aones = tc::make_desc(tc::smem_u32(sm + L.a_ones), 2048, 128);
   const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
   uint32_t phase = 0;
   for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
@@ -174,11 +178,11 @@ __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem&
         tc::fence_after_sync();
         if (lane == 0) {
           if (s2 == 0) {
-            tc_issue_l1(nd, a1h, a1l, tD1, 0, mD1);
-            if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, tD1, 1, mD1);
+            tc_issue_l1(nd, a1h, a1l, aones, tD1, 0, mD1);
+            if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, aones, tD1, 1, mD1);
           } else {
             tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
-            if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, tD1, s2 + 1, mD1);
+            if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, aones, tD1, s2 + 1, mD1);
           }
         }
         __syncwarp();
@@ -195,10 +199,19 @@ __global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigne
   const int tid = threadIdx.x;
   for (uint32_t i = tid; i < L.consts / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
   __syncthreads();
-  tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kWScale, img + L.w1q_hi, img + L.w1q_lo);
-  tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kWScale, img + L.w2q);
-  tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kWScale, img + L.w1g_hi, img + L.w1g_lo);
-  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kWScale, img + L.w2g);
+  tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kW1Scale, img + L.w1q_hi, img + L.w1q_lo);
+  tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kW2Scale, img + L.w2q);
+  tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kW1Scale, img + L.w1g_hi, img + L.w1g_lo);
+  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kW2Scale, img + L.w2g);
+  // layer-1 biases as B operands: row n of K-group 0 = [fp16(16 b), fp16(16 b - hi), 0 ...]; K-group 1 stays zero
+  for (int n = tid; n < H; n += blockDim.x) {
+    const float bq = __ldg(a.q1.b[0] + n) * kW1Scale, bg = __ldg(a.g.b[0] + n) * kW1Scale;
+    const __half qh = __float2half_rn(bq), gh = __float2half_rn(bg);
+    const __half2 q2 = __halves2half2(qh, __float2half_rn(bq - __half2float(qh)));
+    const __half2 g2 = __halves2half2(gh, __float2half_rn(bg - __half2float(gh)));
+    *reinterpret_cast<__half2*>(img + L.w1q_b + (size_t)n * 16) = q2;
+    *reinterpret_cast<__half2*>(img + L.w1g_b + (size_t)n * 16) = g2;
+  }
   float* b1q = reinterpret_cast<float*>(img + L.b1q); float* b2q = reinterpret_cast<float*>(img + L.b2q);
   float* b1g = reinterpret_cast<float*>(img + L.b1g); float* b2g = reinterpret_cast<float*>(img + L.b2g);
   for (int i = tid; i < H; i += blockDim.x) { b1q[i] = __ldg(a.q1.b[0] + i); b1g[i] = __ldg(a.g.b[0] + i); }
@@ -217,9 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform (kept in a uniform register)
   const int nchunk = H / kTcChunk;
 
-  float* sb1q = reinterpret_cast<float*>(sm + L.b1q);
   float* sb2q = reinterpret_cast<float*>(sm + L.b2q);
-  float* sb1g = reinterpret_cast<float*>(sm + L.b1g);
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
@@ -244,6 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
   if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
+    const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
+    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -262,9 +277,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
 
   TcNetDesc nq, ng;
   nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
   nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
   nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
   ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
   ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
   ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
 
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         }
       }
       if (!t0) {
-        tc_mlp_compute(g, x, sb1q, nchunk);
+        tc_mlp_compute(g, x, nchunk);
         float mb[16];
         tc::tmem_ld16(g.tD2, mu1);
         tc::tmem_ld16(g.tD2 + 16, mb);
@@ -364,7 +381,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       }
 
       // ---- emission
-      tc_mlp_compute(g, x, sb1g, nchunk);
+      tc_mlp_compute(g, x, nchunk);
       float gsum = 0.f;
 #pragma unroll
       for (int c = 0; c < NPG; c += 16) {
@@ -411,9 +428,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nchunk = H / kTcChunk;
 
-  float* sb1q = reinterpret_cast<float*>(sm + L.b1q);
   float* sb2q = reinterpret_cast<float*>(sm + L.b2q);
-  float* sb1g = reinterpret_cast<float*>(sm + L.b1g);
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: sp[16] | inv1[16] | inv2[16] | inv_sf[16] | inv_sg[32] | ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
@@ -435,6 +450,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   }
   if (tid >= 32 && tid < 64) C[64 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
   if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
+    const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
+    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -454,9 +473,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
 
   TcNetDesc nq, ng;
   nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
   nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
   nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
   ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
   ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
   ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
 
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
       // ---- f(x_{t+1} | x~)
       float f_lp = 0.0f;
       if (!last) {
-        tc_mlp_compute(g, x, sb1q, nchunk);
+        tc_mlp_compute(g, x, nchunk);
         float muf[16], mb[16];
         tc::tmem_ld16(g.tD2, muf);
         tc::tmem_ld16(g.tD2 + 16, mb);
@@ -535,7 +556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
         f_lp = -0.5f * s - ld_f - cx;
       }
       // ---- g(y_t | x~)
-      tc_mlp_compute(g, x, sb1g, nchunk);
+      tc_mlp_compute(g, x, nchunk);
       float gsum = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < NPG; c0 += 16) {
