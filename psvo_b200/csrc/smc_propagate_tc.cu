@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d] + mb[d], kWUnscale, sb2q[d]);
       } else {
 #pragma unroll
-        for (int d = 0; d < 16; ++d) mu1[d] = d < Dx ? a.mu0[(size_t)b * Dx + d] : 0.0f;
+        for (int d = 0; d < 16; ++d) mu1[d] = d < Dx ? __ldg(a.mu0 + (size_t)b * Dx + d) : 0.0f;
       }
 
       // ---- proposal (fusion), sample, q / f log densities   (f = d1: use_bootstrap, SVO.py:230)
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       for (int d = 0; d < 16; ++d) {
         float m = mu1[d];
         if (two_q) {
-          const float m2 = d < Dx ? a.mu2_all[bt * Dx + d] : 0.0f;
+          const float m2 = d < Dx ? __ldg(a.mu2_all + bt * Dx + d) : 0.0f;
           m = sp[d] * (inv1[d] * mu1[d] + inv2[d] * m2);
         }
         const float X = fmaf(sp[d], e[d], m);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         for (int i = 0; i < 16; ++i) {
           const int d = c + i;
           if (d < Dy) {
-            const float y = a.obs[bt * Dy + d];
+            const float y = __ldg(a.obs + bt * Dy + d);
             const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
             const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
           float xv = 0.0f;
           if (d < Dx) {
             float mean;
-            if (last) mean = a.mu_init_all[bt * Dx + d];
+            if (last) mean = __ldg(a.mu_init_all + bt * Dx + d);
             else {
-              const float m1 = a.mu1i[((size_t)b * N + i) * Dx + d], m2 = a.m2_all[bt * Dx + d];
+              const float m1 = __ldg(a.mu1i + ((size_t)b * N + i) * Dx + d), m2 = __ldg(a.m2_all + bt * Dx + d);
               mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
             }
             xv = mean + sp[d] * e[k];
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
         for (int k = 0; k < 16; ++k) {
           const int d = c0 + k;
           if (d < Dy) {
-            const float y = a.obs[bt * Dy + d];
+            const float y = __ldg(a.obs + bt * Dy + d);
             const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
             const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
