@@ -199,6 +199,13 @@ PSVO_API int psvo_gather(const float* src, const int32_t* idx, int64_t rows, int
 PSVO_API int psvo_mlp_forward(const psvo_mlp* net, const float* x, int64_t rows, float* mu, psvo_stream_t stream);
 PSVO_API int psvo_mlp_backward(const psvo_mlp* net, const float* x, const float* g_mu, int64_t rows,
                       float* g_x, psvo_mlp_grad* grads, psvo_stream_t stream);
+/* psvo_mlp_backward on sm_100a tensor cores (tcgen05, fp16x3 split operands, fp32 accumulation; weight gradients as
+ * GEMMs over the rows with TMEM-resident accumulators).  One hidden layer of width 64/128/192/256, d_in <= 16,
+ * d_out <= 32, rows >= 8192; psvo_mlp_backward_tc_supported() tells.  g_x is overwritten, grads are accumulated. */
+PSVO_API int psvo_mlp_backward_tc_supported(const psvo_mlp* net, int64_t rows);
+PSVO_API size_t psvo_mlp_backward_tc_workspace_bytes(const psvo_mlp* net);
+PSVO_API int psvo_mlp_backward_tc(const psvo_mlp* net, const float* x, const float* g_mu, int64_t rows, float* g_x,
+                         psvo_mlp_grad* grads, void* ws, size_t ws_bytes, psvo_stream_t stream);
 PSVO_API int psvo_get_sigma(const float* sigma_con, float sigma_min, int32_t D, float* sigma, psvo_stream_t stream);
 PSVO_API int psvo_mvn_log_prob(const float* x, const float* mu, const float* sigma, int64_t rows, int32_t D,
                       float* out, psvo_stream_t stream);

@@ -65,6 +65,9 @@ SIGNATURES = {
     "psvo_gather": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "psvo_mlp_forward": (C.c_int, [C.POINTER(psvo_mlp), _vp, _i64, _vp, _vp]),
     "psvo_mlp_backward": (C.c_int, [C.POINTER(psvo_mlp), _vp, _vp, _i64, _vp, C.POINTER(psvo_mlp_grad), _vp]),
+    "psvo_mlp_backward_tc_supported": (C.c_int, [C.POINTER(psvo_mlp), _i64]),
+    "psvo_mlp_backward_tc_workspace_bytes": (_sz, [C.POINTER(psvo_mlp)]),
+    "psvo_mlp_backward_tc": (C.c_int, [C.POINTER(psvo_mlp), _vp, _vp, _i64, _vp, C.POINTER(psvo_mlp_grad), _vp, _sz, _vp]),
     "psvo_get_sigma": (C.c_int, [_vp, _f, _i32, _vp, _vp]),
     "psvo_mvn_log_prob": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "psvo_logsumexp": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),

@@ -99,6 +99,14 @@ struct CandTcArgs {
 bool ffbsi_cand_tc_supported(const psvo_mlp& f, const psvo_mlp& g, int Dx, int Dy, long long rows);
 int launch_ffbsi_cand_tc(const CandTcArgs& a, cudaStream_t st);
 
+// tensor-core (tcgen05) reverse mode of a one-hidden-layer MLP over particle rows (mlp_bwd_tc.cu)
+bool mlp_bwd_tc_supported(const psvo_mlp& net, long long rows);
+size_t mlp_bwd_tc_image_bytes(const psvo_mlp& net);
+int launch_mlp_bwd_tc_stage(const psvo_mlp& net, unsigned char* image, cudaStream_t st);
+int launch_mlp_bwd_tc(const psvo_mlp& net, const unsigned char* image, const float* x, long long x_seq_stride, const float* g,
+                      int B, int N, float* gx, const int* scatter, long long scatter_seq_stride, const psvo_mlp_grad& grads,
+                      unsigned int* gmax_bits, cudaStream_t st);
+
 // tensor-core (tcgen05) one-hidden-layer MLP over particle rows (tc_mlp.cu)
 bool tc_mlp_supported(const psvo_mlp& net);
 int launch_particle_mlp_tc(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, float* out,

@@ -337,8 +337,15 @@ def mlp_backward_raw(Ws, bs, x, g_mu, need_gx=True):
         gr.W[k], gr.b[k] = gW[k].data_ptr(), gb[k].data_ptr()
     gx = torch.empty_like(x) if need_gx else None
     with torch.cuda.device(x.device):
-        L.check(lib.psvo_mlp_backward(C.byref(m), _ptr(x), _ptr(g_mu), rows, _ptr(gx), C.byref(gr), _stream()),
-                "psvo_mlp_backward")
+        if lib.psvo_mlp_backward_tc_supported(C.byref(m), rows):
+            # particle-shaped nets with many rows: reverse mode on the tensor cores (mlp_bwd_tc.cu)
+            gx = torch.empty_like(x)
+            ws = torch.empty(int(lib.psvo_mlp_backward_tc_workspace_bytes(C.byref(m))), device=x.device, dtype=torch.uint8)
+            L.check(lib.psvo_mlp_backward_tc(C.byref(m), _ptr(x), _ptr(g_mu), rows, _ptr(gx), C.byref(gr), _ptr(ws),
+                                             C.c_size_t(ws.numel()), _stream()), "psvo_mlp_backward_tc")
+        else:
+            L.check(lib.psvo_mlp_backward(C.byref(m), _ptr(x), _ptr(g_mu), rows, _ptr(gx), C.byref(gr), _stream()),
+                    "psvo_mlp_backward")
     return gx, gW, gb
 
 

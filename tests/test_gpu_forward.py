@@ -57,7 +57,9 @@ def test_gather_matches_index_select():
 @pytest.mark.parametrize("hidden,din,dout,rows", [([], 4, 4, 37), ([32], 2, 2, 100), ([64, 48], 128, 4, 50), ([256], 32, 16, 513),
                                                    # shapes that take the tcgen05 tensor-core path (d_in<=16, H%16==0, rows>=256)
                                                    ([256], 16, 16, 1000), ([256], 16, 32, 4099), ([64], 4, 1, 300), ([32], 2, 2, 1000),
-                                                   ([128], 3, 3, 256)])
+                                                   ([128], 3, 3, 256),
+                                                   # reverse mode on tensor cores too (H % 64 == 0, rows >= 8192); ragged rows / dims
+                                                   ([256], 16, 32, 8192), ([128], 13, 29, 9001), ([64], 4, 1, 8300), ([192], 5, 16, 20000)])
 def test_mlp_forward_and_backward(hidden, din, dout, rows):
     g = torch.Generator().manual_seed(1)
     net = O.make_net(g, din, hidden, dout)
