@@ -31,6 +31,8 @@ struct BwdArgs {
   const float* obs; const float* mu2_all; const float* mu0; const float* muf0;
   const float* Xs; const float* X_anc; const int* anc; const float* log_Ws; const float* lse;
   const float* g_logZ_b;
+  const float* ext_mu;    // tensor-core path: the network output of every particle (B*N, d_out) computed by a tcgen05
+  float* ext_g;           //   kernel; this kernel then only writes the upstream gradient (B*N, d_out) for mlp_bwd_tc
   const float* g_Xs;      // (B,T,N,Dx) incoming d/dXs (FFBSi reverse mode) or NULL
   const float* g_log_Ws;  // (B,T,N)    incoming d/dlog_Ws or NULL
   float* gXg;        // (B,N,Dx) emission contribution to d/dX_t         (written by bwd_emission)
@@ -61,14 +63,18 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
   const bool poisson = a.flags & PSVO_F_POISSON;
   MlpS<DXP, DYP> gs;
   MlpGradS<DXP, DYP> gg;
+  const bool ext = a.ext_mu != nullptr;      // MLP g forward / reverse run on tensor cores around this kernel
   float* p = smem;
   float* sg = p; p += 32;
   float* sstat = p; p += 32;
-  p = mlp_stage<DXP, DYP>(a.g, p, gs);
-  float* gacc0 = p;
-  p = mlp_grad_carve<DXP, DYP>(a.g, p, gg);
-  for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
   float* stage = p;
+  if (!ext) {
+    p = mlp_stage<DXP, DYP>(a.g, p, gs);
+    float* gacc0 = p;
+    p = mlp_grad_carve<DXP, DYP>(a.g, p, gg);
+    for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
+    stage = p;
+  }
   if (threadIdx.x < 32) { sg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; sstat[threadIdx.x] = 0.0f; }
   __syncthreads();
 
@@ -90,7 +96,12 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
     float xx[1][DXP], mug[1][DYP];
 #pragma unroll
     for (int d = 0; d < DXP; ++d) xx[0][d] = x[d];
-    mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
+    if (ext) {
+#pragma unroll
+      for (int d = 0; d < DYP; ++d) mug[0][d] = (live && d < Dy) ? a.ext_mu[((size_t)b * N + n) * Dy + d] : 0.0f;
+    } else {
+      mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
+    }
     const float gl = particle_weight_grad(a, b, n, live);
     float G[DYP];
 #pragma unroll
@@ -107,6 +118,13 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
           st_sg[d] += gl * (z * z - 1.0f) / sg[d];
         }
       }
+    }
+    if (ext) {
+      if (live) {
+#pragma unroll
+        for (int d = 0; d < DYP; ++d) if (d < Dy) a.ext_g[((size_t)b * N + n) * Dy + d] = G[d];
+      }
+      continue;
     }
     float gx[DXP];
     mlp_bwd_tile<DXP, DYP>(gs, gg, x, G, gx, stage);
@@ -125,7 +143,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
   }
   __syncthreads();
   if (!poisson && threadIdx.x < Dy) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, sstat[threadIdx.x]);
-  mlp_grad_flush<DXP, DYP>(a.g, gg, a.gg);
+  if (!ext) mlp_grad_flush<DXP, DYP>(a.g, gg, a.gg);
 }
 
 template <int DXP>
@@ -143,8 +161,9 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
   float* C = p; p += 5 * DXP;                 // s1 | sf | sp | inv1 | inv2
   float* sred = p; p += 4 * 32;               // block partials: gm2 | gmu1 (t0) | gmuf (t0) | spare
   float* sstat = p; p += 4 * 32;              // SP | I1 | I2 | SF
+  const bool ext = a.ext_mu != nullptr && !t0;   // MLP q1 forward / reverse run on tensor cores around this kernel
   float* gacc0 = p;
-  if (!t0) {
+  if (!t0 && !ext) {
     p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
     if (sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
     gacc0 = p;
@@ -183,8 +202,13 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
     if (!t0) {
 #pragma unroll
       for (int d = 0; d < DXP; ++d) par[0][d] = (live && d < Dx) ? a.X_anc[((bt - 1) * N + n) * Dx + d] : 0.0f;
-      mlp_eval<DXP, DXP, 1>(q1s, par, mu1, nullptr, 0);
-      if (sep_f) mlp_eval<DXP, DXP, 1>(fs, par, muf, nullptr, 0);
+      if (ext) {
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) mu1[0][d] = (live && d < Dx) ? a.ext_mu[bn * Dx + d] : 0.0f;
+      } else {
+        mlp_eval<DXP, DXP, 1>(q1s, par, mu1, nullptr, 0);
+        if (sep_f) mlp_eval<DXP, DXP, 1>(fs, par, muf, nullptr, 0);
+      }
     } else {
 #pragma unroll
       for (int d = 0; d < DXP; ++d) {
@@ -252,7 +276,12 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
       }
     }
 
-    if (!t0) {
+    if (ext) {
+      if (live) {
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) if (d < Dx) a.ext_g[bn * Dx + d] = gmu1[d];
+      }
+    } else if (!t0) {
       float ga[DXP], ga2[DXP];
       mlp_bwd_tile<DXP, DXP>(q1s, gq1, par[0], gmu1, ga, stage);
       if (sep_f) {
@@ -287,7 +316,7 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
     atomicAdd(a.stats + (ST_I2 * 2 + tau) * 32 + d, sstat[64 + d]);
     atomicAdd(a.stats + (ST_SF * 2 + tau) * 32 + d, sstat[96 + d]);
   }
-  if (!t0) {
+  if (!t0 && !ext) {
     mlp_grad_flush<DXP, DXP>(a.q1, gq1, a.gq1);
     if (sep_f) mlp_grad_flush<DXP, DXP>(a.f, gf, a.gf);
   }
@@ -366,8 +395,19 @@ static size_t staged_floats(const psvo_mlp& net, int din_pad, int dout_pad) {
   return (size_t)net.width[0] * din_pad + round4(net.width[0]) + (size_t)net.width[0] * dout_pad + dout_pad;
 }
 
-struct BwdWs { float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp; size_t bytes; };
-static BwdWs carve_bwd(const psvo_dims* d, char* base) {
+struct BwdWs {
+  float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp;
+  float *tc_mu, *tc_g; unsigned char *img_g, *img_q1; unsigned int* gmax;     // tensor-core reverse mode (or NULL)
+  size_t bytes;
+};
+static bool tc_backward_ok(const psvo_dims* d, const psvo_params* p) {
+  if (p == nullptr) return false;
+  if (!(d->flags & PSVO_F_BOOTSTRAP) || !(d->flags & PSVO_F_TWO_Q)) return false;      // f aliases d1: one network per step side
+  const long long rows = (long long)d->B * d->N;
+  return mlp_bwd_tc_supported(p->q1.net, rows) && mlp_bwd_tc_supported(p->g.net, rows) && tc_mlp_supported(p->q1.net) &&
+         tc_mlp_supported(p->g.net) && rows < (1LL << 31);
+}
+static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
   BwdWs w;
   size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
@@ -378,6 +418,14 @@ static BwdWs carve_bwd(const psvo_dims* d, char* base) {
   w.gXa = take(BN * d->Dx); w.gXb = take(BN * d->Dx); w.gXg = take(BN * d->Dx);
   w.stats = take(ST_SLOTS * 2 * 32);
   w.gx0tmp = take((size_t)d->B * d->Dx0);
+  w.tc_mu = w.tc_g = nullptr; w.img_g = w.img_q1 = nullptr; w.gmax = nullptr;
+  if (tc_backward_ok(d, p)) {
+    const size_t wide = d->Dx > d->Dy ? d->Dx : d->Dy;
+    w.tc_mu = take(BN * wide); w.tc_g = take(BN * wide);
+    w.img_g = reinterpret_cast<unsigned char*>(take(mlp_bwd_tc_image_bytes(p->g.net) / sizeof(float) + 64));
+    w.img_q1 = reinterpret_cast<unsigned char*>(take(mlp_bwd_tc_image_bytes(p->q1.net) / sizeof(float) + 64));
+    w.gmax = reinterpret_cast<unsigned int*>(take(64));
+  }
   w.bytes = off;
   return w;
 }
@@ -397,9 +445,8 @@ using namespace psvo;
 extern "C" {
 
 PSVO_API size_t psvo_smc_backward_workspace_bytes(const psvo_dims* d, const psvo_params* p) {
-  (void)p;
   if (d == nullptr) return 0;
-  return carve_bwd(d, nullptr).bytes;
+  return carve_bwd(d, p, nullptr).bytes;
 }
 
 PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const float* obs, const float* pre_obs,
@@ -419,7 +466,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   const psvo_dist& fd = boot ? p->q1 : p->f;
   PSVO_REQUIRE(p->q1.net.n_hidden <= 1 && p->g.net.n_hidden <= 1 && fd.net.n_hidden <= 1,
                "psvo_smc_backward: per-particle networks (q1, f, g) with more than one hidden layer are not supported by the reverse-mode kernels yet");
-  const BwdWs w = carve_bwd(d, static_cast<char*>(ws));
+  const BwdWs w = carve_bwd(d, p, static_cast<char*>(ws));
   PSVO_REQUIRE(ws_bytes >= w.bytes, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const int B = d->B, T = d->T, N = d->N, Dx = d->Dx;
@@ -472,11 +519,61 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
     return (int)(work < cap ? work : cap);
   };
 
+  // tensor-core reverse mode (default flags, one hidden layer of 64..256 units, >= 8192 particles per step): the two
+  // per-particle networks run as  tcgen05 forward (mu) -> this file's kernels without their MLP part (upstream gradient,
+  // sigma statistics, per-sequence reductions) -> tcgen05 reverse (mlp_bwd_tc.cu: gx, dW, db)
+  const bool tc = w.tc_mu != nullptr;
+  int blkEx = 0, blkPx = 0; size_t smEx = 0, smPx = 0;
+  if (tc) {
+    PSVO_CUDA(cudaMemsetAsync(w.img_g, 0, mlp_bwd_tc_image_bytes(a.g), st));
+    PSVO_CUDA(cudaMemsetAsync(w.img_q1, 0, mlp_bwd_tc_image_bytes(a.q1), st));
+    if (int e = launch_mlp_bwd_tc_stage(a.g, w.img_g, st)) return e;
+    if (int e = launch_mlp_bwd_tc_stage(a.q1, w.img_q1, st)) return e;
+    blkEx = blkPx = 256;                      // without their MLP part the kernels only need their constant blocks
+    smEx = 64 * sizeof(float); smPx = (5 * DXP + 256) * sizeof(float);
+  }
+  a.ext_mu = nullptr; a.ext_g = nullptr;
+
   float* gXin = w.gXa;      // children contribution for the current step (zero at t = T-1)
   float* gXout = w.gXb;
   for (int t = T - 1; t >= 0; --t) {
     a.t = t; a.gXin = gXin; a.gXout = gXout;
     if (t > 0) PSVO_CUDA(cudaMemsetAsync(gXout, 0, BN * Dx * sizeof(float), st));
+    if (tc) {
+      const long long sstr = (long long)T * N * Dx;
+      const float* Xt = Xs + (size_t)t * N * Dx;
+      int rc = 0;
+      // ---- emission side
+      if ((rc = launch_particle_mlp_tc(a.g, Xt, sstr, B, N, w.tc_mu, st))) return rc;
+      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g;
+      rc = -1;
+#define PSVO_CASE_EX(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkEx, grid_of(blkEx, smEx), smEx, st);
+      PSVO_CASE_EX(4, 4) PSVO_CASE_EX(4, 8) PSVO_CASE_EX(4, 16) PSVO_CASE_EX(4, 32)
+      PSVO_CASE_EX(8, 4) PSVO_CASE_EX(8, 8) PSVO_CASE_EX(8, 16) PSVO_CASE_EX(8, 32)
+      PSVO_CASE_EX(16, 4) PSVO_CASE_EX(16, 8) PSVO_CASE_EX(16, 16) PSVO_CASE_EX(16, 32)
+#undef PSVO_CASE_EX
+      if (rc) return rc;
+      if ((rc = launch_mlp_bwd_tc(a.g, w.img_g, Xt, sstr, w.tc_g, B, N, w.gXg, nullptr, 0, a.gg, w.gmax, st))) return rc;
+      // ---- proposal side
+      if (t > 0) {
+        const float* Xp = X_anc + (size_t)(t - 1) * N * Dx;
+        if ((rc = launch_particle_mlp_tc(a.q1, Xp, sstr, B, N, w.tc_mu, st))) return rc;
+        rc = DXP == 4 ? launch_proposal_t<4>(a, blkPx, grid_of(blkPx, smPx), smPx, st)
+                      : (DXP == 8 ? launch_proposal_t<8>(a, blkPx, grid_of(blkPx, smPx), smPx, st)
+                                  : launch_proposal_t<16>(a, blkPx, grid_of(blkPx, smPx), smPx, st));
+        if (rc) return rc;
+        if ((rc = launch_mlp_bwd_tc(a.q1, w.img_q1, Xp, sstr, w.tc_g, B, N, gXout, anc + (size_t)(t - 1) * N, (long long)T * N,
+                                    a.gq1, w.gmax, st))) return rc;
+      } else {
+        a.ext_mu = nullptr; a.ext_g = nullptr;             // t = 0: no per-particle proposal network (q0 is per sequence)
+        rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP, smP), smP, st)
+                      : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
+                                  : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
+        if (rc) return rc;
+      }
+      float* tmp = gXin; gXin = gXout; gXout = tmp;
+      continue;
+    }
     int rc = -1;
 #define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, grid_of(blkE, smE), smE, st);
     PSVO_CASE_E(4, 4) PSVO_CASE_E(4, 8) PSVO_CASE_E(4, 16) PSVO_CASE_E(4, 32)

@@ -23,6 +23,10 @@ CASES = [
     ("noboot", 3, 2, 4, 3, [16], 100, 2, 4, O.Flags(use_bootstrap=False)),
     ("neither", 4, 2, 2, 4, [16], 130, 2, 4, O.Flags(use_bootstrap=False, use_2_q=False)),
     ("one_particle", 2, 1, 1, 1, [8], 1, 2, 3, O.Flags()),
+    # >= 8192 particles per step, H in {64,128,192,256}, default flags: the tcgen05 reverse mode (mlp_bwd_tc.cu)
+    ("c5_shape_tensor_core", 16, 32, 32, 32, [256], 4096, 2, 3, O.Flags()),
+    ("tensor_core_ragged", 5, 7, 6, 9, [128], 3000, 3, 3, O.Flags()),
+    ("tensor_core_poisson_h64", 4, 1, 8, 8, [64], 2100, 4, 3, O.Flags(poisson_emission=True)),
 ]
 
 
