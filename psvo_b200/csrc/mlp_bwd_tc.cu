@@ -9,7 +9,7 @@
 //     per 128-row tile and per chunk of 64 hidden units
 //       L1  : D1[128 x 64] = x      * W1c          (K = 16)            row-wise, K-major operands
 //       dh  : D3[128 x 64] = G      * W2c^T        (K = d_out)         row-wise
-//       dx  : DX[128 x 16]+= gpre_c * W1c^T        (K = 64)            row-wise
+//       dx  : DX[128 x 16]+= gpre_c * W1c^T        (K = 64)            row-wise; B = the L1 operand W1 read MN-major
 //       dW2 : AW2c[64 x NP]  += h_c^T    * G       (K = 128 rows)      MN-major operands (see below), M = 64
 //       dW1 : AW1c[64 x 24]  += gpre_c^T * [x | 1] (K = 128 rows)      MN-major; the ones column yields db1
 // The weight-gradient GEMMs contract over the ROWS.  Their operands are read straight from the row-wise buffers the
@@ -18,12 +18,13 @@
 // profiles/microbench/umma_mnmajor_test.cu, which also gives the M = 64 accumulator lane map: row r -> lane (r/16)*32 + r%16).
 // The weight-gradient accumulators stay in TMEM for all tiles of the (persistent) CTA and are flushed once.
 //
-// Scales (exact powers of two): W1 x16, W2 x256, W1^T x256, G x sG with sG chosen from max|G| of the launch so that the
+// Scales (exact powers of two): W1 x16 (also read MN-major as the B operand of dx), W2 x256, G x sG with sG chosen from max|G| of the launch so that the
 // fp16 lo halves stay normal; every accumulator is un-scaled in fp32 when it is read.
 //
-// CTA = 128 compute threads (TMEM lane == row == thread) + one MMA-issuing warp.  One CTA per SM (the accumulators take the
+// CTA = 256 compute threads (TMEM lane == row; two threads per row split the columns of every chunk) + three MMA-issuing
+// warps (row-wise products, dW2, dW1).  One CTA per SM (the accumulators take the
 // TMEM): this first version overlaps the big weight-gradient MMAs of chunk c with the epilogue arithmetic of chunk c+1
-// only through the early issue of L1/dh; shared-memory operands are single-buffered.
+// through the early issue of L1/dh and through double-buffered h / gpre operands.
 #include <stdlib.h>
 #include "smc_kernels.h"
 #include "tc_common.cuh"
@@ -31,10 +32,14 @@
 namespace psvo {
 
 constexpr int kBtChunk = 64;
+// stride between the 8-column groups of a row-operand buffer: 128 rows x 16 B plus 16 B of padding, so that the 8 (or 4, 3)
+// column groups an MN-major MMA reads for one k land in different shared-memory banks (no-swizzle layout)
+constexpr int kBtGrp = 2048 + 16;
+constexpr int kBtBuf = 8 * kBtGrp;       // one chunk (64 columns) of a row operand
 constexpr float kBtW1Scale = 16.0f, kBtW2Scale = 256.0f;
 
 struct BtSmem {
-  uint32_t w1_hi, w1_lo, w2_hi, w2_lo, w1t_hi, w1t_lo, b1s, image_end;
+  uint32_t w1_hi, w1_lo, w2_hi, w2_lo, b1s, image_end;
   uint32_t x_hi, x_lo, g_hi, g_lo, hc_hi, hc_lo, gp_hi, gp_lo, db2, bars, slot, total;
 };
 __host__ __device__ inline BtSmem bt_layout(int H, int NP) {
@@ -42,13 +47,12 @@ __host__ __device__ inline BtSmem bt_layout(int H, int NP) {
 #define PSVO_TAKE(bytes) (o += (((bytes) + 127u) & ~127u), o - (((bytes) + 127u) & ~127u))
   s.w1_hi = PSVO_TAKE(H * 32); s.w1_lo = PSVO_TAKE(H * 32);
   s.w2_hi = PSVO_TAKE(H * NP * 2); s.w2_lo = PSVO_TAKE(H * NP * 2);
-  s.w1t_hi = PSVO_TAKE(H * 32); s.w1t_lo = PSVO_TAKE(H * 32);
   s.b1s = PSVO_TAKE(H * 4);
   s.image_end = o;
-  s.x_hi = PSVO_TAKE(3 * 2048); s.x_lo = PSVO_TAKE(3 * 2048);
-  s.g_hi = PSVO_TAKE((NP / 8) * 2048); s.g_lo = PSVO_TAKE((NP / 8) * 2048);
-  s.hc_hi = PSVO_TAKE(8 * 2048); s.hc_lo = PSVO_TAKE(8 * 2048);
-  s.gp_hi = PSVO_TAKE(8 * 2048); s.gp_lo = PSVO_TAKE(8 * 2048);
+  s.x_hi = PSVO_TAKE(3 * kBtGrp); s.x_lo = PSVO_TAKE(3 * kBtGrp);
+  s.g_hi = PSVO_TAKE((NP / 8) * kBtGrp); s.g_lo = PSVO_TAKE((NP / 8) * kBtGrp);
+  s.hc_hi = PSVO_TAKE(2 * kBtBuf); s.hc_lo = PSVO_TAKE(2 * kBtBuf);     // double-buffered over chunks
+  s.gp_hi = PSVO_TAKE(2 * kBtBuf); s.gp_lo = PSVO_TAKE(2 * kBtBuf);
   s.db2 = PSVO_TAKE(32 * 4);
   s.bars = PSVO_TAKE(8 * 8); s.slot = PSVO_TAKE(16);
 #undef PSVO_TAKE
@@ -75,7 +79,6 @@ __global__ void __launch_bounds__(512) mlp_bwd_tc_stage_kernel(psvo_mlp net, int
   const BtSmem L = bt_layout(H, NP);
   bt_stage_b(net.W[0], H, din, 1, H, H, 16, kBtW1Scale, img + L.w1_hi, img + L.w1_lo);         // (j, d) = W1[d][j]
   bt_stage_b(net.W[1], H, dout, dout, 1, H, NP, kBtW2Scale, img + L.w2_hi, img + L.w2_lo);     // (j, o) = W2[j][o]
-  bt_stage_b(net.W[0], din, H, H, 1, 16, H, kBtW2Scale, img + L.w1t_hi, img + L.w1t_lo);       // (d, j) = W1[d][j]
   float* b1s = reinterpret_cast<float*>(img + L.b1s);
   for (int i = threadIdx.x; i < H; i += blockDim.x) b1s[i] = __ldg(net.b[0] + i) * kBtW1Scale;
 }
@@ -105,7 +108,7 @@ __device__ __forceinline__ void bt_mma3(uint32_t d, uint64_t ah, uint64_t al, ui
   tc::mma_bf16(d, al, bh, idesc, true);
 }
 
-__global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
+__global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
   const int H = a.H, NP = a.NP, din = a.d_in, dout = a.d_out, N = a.N;
   const BtSmem L = bt_layout(H, NP);
@@ -117,8 +120,8 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
   uint64_t* d_ready = bars + 1;    // commit       : L1(c) + dh(c) complete
   uint64_t* d_read = bars + 2;     // 128 arrivals : D1 / D3 of chunk c are in registers
   uint64_t* a_ready = bars + 3;    // 128 arrivals : h / gpre operands of chunk c staged
-  uint64_t* a_free = bars + 4;     // commit       : the MMAs reading them complete
-  uint64_t* dx_done = bars + 5;    // commit       : DX of the tile complete
+  uint64_t* a_free = bars + 4;     // [2] commits  : the MMAs reading operand buffer 0 / 1 complete (one commit per MMA warp)
+  uint64_t* dx_done = bars + 6;    // commit       : DX of the tile complete
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
   float* sdb2 = reinterpret_cast<float*>(sm + L.db2);
   const float* sb1 = reinterpret_cast<const float*>(sm + L.b1s);
@@ -129,13 +132,13 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
     for (int i = tid; i < (int)(L.image_end / 16); i += blockDim.x) dst[i] = __ldg(src + i);
   }
   if (tid < 128) {     // constant parts of the x operands: K-group 2 = the ones column (hi) / zeros (lo)
-    *reinterpret_cast<uint4*>(sm + L.x_hi + 2 * 2048 + tid * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);      // half 1.0 at d = 16
-    *reinterpret_cast<uint4*>(sm + L.x_lo + 2 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sm + L.x_hi + 2 * kBtGrp + tid * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);      // half 1.0 at d = 16
+    *reinterpret_cast<uint4*>(sm + L.x_lo + 2 * kBtGrp + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid < 32) sdb2[tid] = 0.0f;
   if (tid == 0) {
-    tc::mbar_init(xg_full, 128); tc::mbar_init(d_ready, 1); tc::mbar_init(d_read, 128);
-    tc::mbar_init(a_ready, 128); tc::mbar_init(a_free, 1); tc::mbar_init(dx_done, 1);
+    tc::mbar_init(xg_full, 256); tc::mbar_init(d_ready, 1); tc::mbar_init(d_read, 256);
+    tc::mbar_init(a_ready, 256); tc::mbar_init(a_free, 3); tc::mbar_init(a_free + 1, 3); tc::mbar_init(dx_done, 1);
   }
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
@@ -152,10 +155,15 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
   if (gmax > 0.0f && gmax < 1e30f) { int e; frexpf(gmax, &e); sG = ldexpf(1.0f, 6 - e); }     // max |G| * sG in [32, 64)
   const float inv_sG = 1.0f / sG;
 
-  if (warp == 4) {
-    // =============================== MMA issuer ===============================
+  if (warp >= 8) {
+    // =============================== MMA issuers ===============================
+    // tcgen05.mma issue costs ~10^2 cycles per instruction and per issuing thread and this kernel is issue-bound (69 MMAs
+    // per chunk), so three warps issue side by side, each owning its accumulators:
+    //   warp 8: row-wise products L1 / dh / dx      warp 9: dW2_c = h_c^T G      warp 10: dW1_c = gpre_c^T [x | 1]
+    // a_free counts one commit per warp.
     if (lane == 0) {
-      const uint32_t id_row64 = tc::make_idesc_f16(128, 64), id_row16 = tc::make_idesc_f16(128, 16);
+      const uint32_t id_row64 = tc::make_idesc_f16(128, 64);
+      const uint32_t id_dx = tc::make_idesc_f16(128, 16) | (1u << 16);      // B = W1 (the L1 operand) read MN-major: (d, j)
       const uint32_t id_w2 = tc::make_idesc_f16(64, NP) | (1u << 15) | (1u << 16);
       const uint32_t id_w1 = tc::make_idesc_f16(64, 24) | (1u << 15) | (1u << 16);
       const uint32_t s_xh = tc::smem_u32(sm + L.x_hi), s_xl = tc::smem_u32(sm + L.x_lo);
@@ -164,65 +172,82 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
       const uint32_t s_ph = tc::smem_u32(sm + L.gp_hi), s_pl = tc::smem_u32(sm + L.gp_lo);
       const uint32_t s_w1h = tc::smem_u32(sm + L.w1_hi), s_w1l = tc::smem_u32(sm + L.w1_lo);
       const uint32_t s_w2h = tc::smem_u32(sm + L.w2_hi), s_w2l = tc::smem_u32(sm + L.w2_lo);
-      const uint32_t s_wth = tc::smem_u32(sm + L.w1t_hi), s_wtl = tc::smem_u32(sm + L.w1t_lo);
       auto issue_l1_dh = [&](int c) {
         // L1: A = x (K = 16), B = W1 rows [c*64, c*64+64)
-        bt_mma3(tD1, tc::make_desc(s_xh, 2048, 128), tc::make_desc(s_xl, 2048, 128),
+        bt_mma3(tD1, tc::make_desc(s_xh, kBtGrp, 128), tc::make_desc(s_xl, kBtGrp, 128),
                 tc::make_desc(s_w1h + c * 64 * 16, H * 16, 128), tc::make_desc(s_w1l + c * 64 * 16, H * 16, 128), id_row64, false);
         // dh: A = G (K = NP), B = W2 rows [c*64, ...)
         for (int ks = 0; ks < NP / 16; ++ks)
-          bt_mma3(tD3, tc::make_desc(s_gh + ks * 4096, 2048, 128), tc::make_desc(s_gl + ks * 4096, 2048, 128),
+          bt_mma3(tD3, tc::make_desc(s_gh + ks * 2 * kBtGrp, kBtGrp, 128), tc::make_desc(s_gl + ks * 2 * kBtGrp, kBtGrp, 128),
                   tc::make_desc(s_w2h + c * 64 * 16 + ks * 2 * H * 16, H * 16, 128),
                   tc::make_desc(s_w2l + c * 64 * 16 + ks * 2 * H * 16, H * 16, 128), id_row64, ks > 0);
         tc::mma_commit(d_ready);
       };
       uint32_t n_tile = 0, n_chunk = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-        tc::mbar_wait(xg_full, n_tile & 1u);
-        tc::fence_after_sync();
-        issue_l1_dh(0);
-        for (int c = 0; c < nch; ++c, ++n_chunk) {
-          tc::mbar_wait(d_read, n_chunk & 1u);
+        if (warp == 8) {
+          tc::mbar_wait(xg_full, n_tile & 1u);
           tc::fence_after_sync();
-          if (c + 1 < nch) issue_l1_dh(c + 1);
+          issue_l1_dh(0);
+        }
+        for (int c = 0; c < nch; ++c, ++n_chunk) {
+          if (warp == 8) {
+            tc::mbar_wait(d_read, n_chunk & 1u);
+            tc::fence_after_sync();
+            if (c + 1 < nch) issue_l1_dh(c + 1);
+          }
           tc::mbar_wait(a_ready, n_chunk & 1u);
           tc::fence_after_sync();
-          // dx: A = gpre_c (K = 64), B = W1^T (16 rows, K-groups c*8 ...)
-          for (int ks = 0; ks < 4; ++ks)
-            bt_mma3(tDX, tc::make_desc(s_ph + ks * 4096, 2048, 128), tc::make_desc(s_pl + ks * 4096, 2048, 128),
-                    tc::make_desc(s_wth + (c * 8 + ks * 2) * 256, 256, 128), tc::make_desc(s_wtl + (c * 8 + ks * 2) * 256, 256, 128),
-                    id_row16, c > 0 || ks > 0);
-          if (c == nch - 1) tc::mma_commit(dx_done);
-          // dW2_c = h_c^T G and dW1_c = gpre_c^T [x | 1]: K = the 128 rows, 8 K-steps of 16 rows (256 B each), MN-major
-          for (int ks = 0; ks < 8; ++ks) {
-            const bool acc = n_tile > 0 || ks > 0;
-            bt_mma3(tW2 + c * 32, tc::make_desc(s_hh + ks * 256, 128, 2048), tc::make_desc(s_hl + ks * 256, 128, 2048),
-                    tc::make_desc(s_gh + ks * 256, 128, 2048), tc::make_desc(s_gl + ks * 256, 128, 2048), id_w2, acc);
-            bt_mma3(tW1 + c * 32, tc::make_desc(s_ph + ks * 256, 128, 2048), tc::make_desc(s_pl + ks * 256, 128, 2048),
-                    tc::make_desc(s_xh + ks * 256, 128, 2048), tc::make_desc(s_xl + ks * 256, 128, 2048), id_w1, acc);
+          const uint32_t bo = (n_chunk & 1u) * kBtBuf;                    // operand buffer of this chunk
+          if (warp == 8) {
+            // dx: A = gpre_c (K = 64, K-major), B = W1 columns [c*64, c*64+64) read MN-major as (d, j)
+            for (int ks = 0; ks < 4; ++ks)
+              bt_mma3(tDX, tc::make_desc(s_ph + bo + ks * 2 * kBtGrp, kBtGrp, 128), tc::make_desc(s_pl + bo + ks * 2 * kBtGrp, kBtGrp, 128),
+                      tc::make_desc(s_w1h + (c * 64 + ks * 16) * 16, 128, H * 16), tc::make_desc(s_w1l + (c * 64 + ks * 16) * 16, 128, H * 16),
+                      id_dx, c > 0 || ks > 0);
+            if (c == nch - 1) tc::mma_commit(dx_done);
+          } else {
+            // weight gradients: K = the 128 rows, 8 K-steps of 16 rows (256 B each), both operands MN-major
+            for (int ks = 0; ks < 8; ++ks) {
+              const bool acc = n_tile > 0 || ks > 0;
+              if (warp == 9)
+                bt_mma3(tW2 + c * 32, tc::make_desc(s_hh + bo + ks * 256, 128, kBtGrp), tc::make_desc(s_hl + bo + ks * 256, 128, kBtGrp),
+                        tc::make_desc(s_gh + ks * 256, 128, kBtGrp), tc::make_desc(s_gl + ks * 256, 128, kBtGrp), id_w2, acc);
+              else
+                bt_mma3(tW1 + c * 32, tc::make_desc(s_ph + bo + ks * 256, 128, kBtGrp), tc::make_desc(s_pl + bo + ks * 256, 128, kBtGrp),
+                        tc::make_desc(s_xh + ks * 256, 128, kBtGrp), tc::make_desc(s_xl + ks * 256, 128, kBtGrp), id_w1, acc);
+            }
           }
-          tc::mma_commit(a_free);
+          tc::mma_commit(a_free + (n_chunk & 1u));
         }
       }
     }
     __syncwarp();
   } else {
-    // =============================== compute threads (thread = row) ===============================
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    unsigned char* px_h = sm + L.x_hi + tid * 16; unsigned char* px_l = sm + L.x_lo + tid * 16;
-    unsigned char* pg_h = sm + L.g_hi + tid * 16; unsigned char* pg_l = sm + L.g_lo + tid * 16;
-    unsigned char* ph_h = sm + L.hc_hi + tid * 16; unsigned char* ph_l = sm + L.hc_lo + tid * 16;
-    unsigned char* pp_h = sm + L.gp_hi + tid * 16; unsigned char* pp_l = sm + L.gp_lo + tid * 16;
+    // =============================== compute threads: two per row ===============================
+    // row = tid & 127 (TMEM lane), half = tid >> 7: warp w and warp w + 4 share a lane quarter and split the columns --
+    // half 0 takes hidden units [0, 32) of every chunk and stages x, half 1 takes [32, 64) and stages G
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    unsigned char* px_h = sm + L.x_hi + row * 16; unsigned char* px_l = sm + L.x_lo + row * 16;
+    unsigned char* pg_h = sm + L.g_hi + row * 16; unsigned char* pg_l = sm + L.g_lo + row * 16;
+    unsigned char* ph_h = sm + L.hc_hi + half * 4 * kBtGrp + row * 16; unsigned char* ph_l = sm + L.hc_lo + half * 4 * kBtGrp + row * 16;
+    unsigned char* pp_h = sm + L.gp_hi + half * 4 * kBtGrp + row * 16; unsigned char* pp_l = sm + L.gp_lo + half * 4 * kBtGrp + row * 16;
     uint32_t n_tile = 0, n_chunk = 0;
+    // every MMA issued for chunks < k complete: the last users of both operand buffers committed
+    auto wait_all_mmas = [&](uint32_t k) {
+      tc::mbar_wait(a_free + ((k - 1) & 1u), ((k - 1) >> 1) & 1u);
+      if (k >= 2) tc::mbar_wait(a_free + ((k - 2) & 1u), ((k - 2) >> 1) & 1u);
+      tc::fence_after_sync();
+    };
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++n_tile) {
-      const long long r = (long long)tile * 128 + tid;
+      const long long r = (long long)tile * 128 + row;
       const bool live = r < rows;
       const int b = live ? (int)(r / N) : 0, n = live ? (int)(r - (long long)b * N) : 0;
-      // the previous tile's MMAs still read x / G (weight gradients of its last chunk): wait for them
-      if (n_tile > 0) { tc::mbar_wait(a_free, (n_chunk - 1) & 1u); tc::fence_after_sync(); }
-      {
+      // the previous tile's MMAs still read x / G (weight gradients of its last two chunks): wait for them
+      if (n_tile > 0) { wait_all_mmas(n_chunk); }
+      if (half == 0) {
         const float* xr = a.x + (long long)b * a.x_seq_stride + (long long)n * din;
-        const float* gr = a.g + r * dout;
 #pragma unroll
         for (int kg = 0; kg < 2; ++kg) {
           float v[8];
@@ -230,8 +255,10 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
           for (int i = 0; i < 8; ++i) v[i] = (live && kg * 8 + i < din) ? xr[kg * 8 + i] : 0.0f;
           uint4 hi, lo;
           tc::split8_f16(v, hi, lo);
-          *reinterpret_cast<uint4*>(px_h + kg * 2048) = hi; *reinterpret_cast<uint4*>(px_l + kg * 2048) = lo;
+          *reinterpret_cast<uint4*>(px_h + kg * kBtGrp) = hi; *reinterpret_cast<uint4*>(px_l + kg * kBtGrp) = lo;
         }
+      } else {
+        const float* gr = a.g + r * dout;
         for (int kg = 0; kg < NP / 8; ++kg) {
           float v[8];
 #pragma unroll
@@ -244,7 +271,7 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
           }
           uint4 hi, lo;
           tc::split8_f16(v, hi, lo);
-          *reinterpret_cast<uint4*>(pg_h + kg * 2048) = hi; *reinterpret_cast<uint4*>(pg_l + kg * 2048) = lo;
+          *reinterpret_cast<uint4*>(pg_h + kg * kBtGrp) = hi; *reinterpret_cast<uint4*>(pg_l + kg * kBtGrp) = lo;
         }
       }
       tc::fence_proxy_async();
@@ -254,13 +281,13 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
       for (int c = 0; c < nch; ++c, ++n_chunk) {
         tc::mbar_wait(d_ready, n_chunk & 1u);
         tc::fence_after_sync();
-        uint4 hh[8], hl[8], gh[8], gl[8];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        uint4 hh[4], hl[4], gh[4], gl[4];
+        {
           float v1[32], v3[32];
           tc::tmem_ld32(tD1 + lane_base + half * 32, v1);
           tc::tmem_ld32(tD3 + lane_base + half * 32, v3);
-          if (half == 1) { tc::fence_before_sync(); tc::mbar_arrive(d_read); }     // D1 / D3 may be overwritten
+          tc::fence_before_sync();
+          tc::mbar_arrive(d_read);                                             // D1 / D3 may be overwritten
           const float* bias = sb1 + c * kBtChunk + half * 32;
 #pragma unroll
           for (int kg = 0; kg < 4; ++kg) {
@@ -271,45 +298,48 @@ __global__ void __launch_bounds__(160, 1) mlp_bwd_tc_kernel(BtArgs a) {
               hv[i] = fmaxf(pre, 0.0f);
               gv[i] = pre > 0.0f ? v3[kg * 8 + i] * (1.0f / kBtW2Scale) : 0.0f;   // sG * gpre
             }
-            tc::split8_f16(hv, hh[half * 4 + kg], hl[half * 4 + kg]);
-            tc::split8_f16(gv, gh[half * 4 + kg], gl[half * 4 + kg]);
+            tc::split8_f16(hv, hh[kg], hl[kg]);
+            tc::split8_f16(gv, gh[kg], gl[kg]);
           }
         }
-        if (c > 0) { tc::mbar_wait(a_free, (n_chunk - 1) & 1u); tc::fence_after_sync(); }   // operands of chunk c-1 consumed
+        const uint32_t buf = n_chunk & 1u, use = n_chunk >> 1;
+        if (use > 0) { tc::mbar_wait(a_free + buf, (use - 1) & 1u); tc::fence_after_sync(); }   // previous user of this buffer done
+        const uint32_t bo = buf * kBtBuf;
 #pragma unroll
-        for (int kg = 0; kg < 8; ++kg) {
-          *reinterpret_cast<uint4*>(ph_h + kg * 2048) = hh[kg]; *reinterpret_cast<uint4*>(ph_l + kg * 2048) = hl[kg];
-          *reinterpret_cast<uint4*>(pp_h + kg * 2048) = gh[kg]; *reinterpret_cast<uint4*>(pp_l + kg * 2048) = gl[kg];
+        for (int kg = 0; kg < 4; ++kg) {
+          *reinterpret_cast<uint4*>(ph_h + bo + kg * kBtGrp) = hh[kg]; *reinterpret_cast<uint4*>(ph_l + bo + kg * kBtGrp) = hl[kg];
+          *reinterpret_cast<uint4*>(pp_h + bo + kg * kBtGrp) = gh[kg]; *reinterpret_cast<uint4*>(pp_l + bo + kg * kBtGrp) = gl[kg];
         }
         tc::fence_proxy_async();
         tc::fence_before_sync();
         tc::mbar_arrive(a_ready);
       }
 
-      // ---- gx = gpre W1^T
+      // ---- gx = gpre W1^T  (half 0 writes dims [0, 8), half 1 dims [8, 16))
       tc::mbar_wait(dx_done, n_tile & 1u);
       tc::fence_after_sync();
       float dx[16];
       tc::tmem_ld16(tDX + lane_base, dx);
       tc::fence_before_sync();
       if (live) {
-        const float un = inv_sG * (1.0f / kBtW2Scale);
+        const float un = inv_sG * (1.0f / kBtW1Scale);                     // DX = 16 sG (gpre W1^T)
+        const int d0 = half * 8, d1 = min(din, d0 + 8);
         if (a.scatter != nullptr) {
           const int parent = a.scatter[(long long)b * a.scatter_seq_stride + n];
           float* dst = a.gx + ((long long)b * N + parent) * din;
-          for (int d = 0; d < din; ++d) atomicAdd(dst + d, dx[d] * un);
+          for (int d = d0; d < d1; ++d) atomicAdd(dst + d, dx[d] * un);
         } else {
           float* dst = a.gx + r * din;
-          for (int d = 0; d < din; ++d) dst[d] = dx[d] * un;
+          for (int d = d0; d < d1; ++d) dst[d] = dx[d] * un;
         }
       }
     }
 
     // ---- flush the weight-gradient accumulators (all MMAs of this CTA complete)
-    if (n_chunk > 0) { tc::mbar_wait(a_free, (n_chunk - 1) & 1u); tc::fence_after_sync(); }
+    if (n_chunk > 0) wait_all_mmas(n_chunk);
     if (n_chunk > 0) {
-      const bool owner = (tid & 31) < 16;                           // M = 64 accumulator: row r lives in lane (r/16)*32 + r%16
-      const int jl = (tid >> 5) * 16 + (tid & 15);
+      const bool owner = (tid & 31) < 16 && half == 0;              // M = 64 accumulator: row r lives in lane (r/16)*32 + r%16
+      const int jl = ((tid >> 5) & 3) * 16 + (tid & 15);
       const float un2 = inv_sG * (1.0f / kBtW1Scale);
       for (int c = 0; c < nch; ++c) {
         const int j = c * kBtChunk + jl;
@@ -376,7 +406,7 @@ int launch_mlp_bwd_tc(const psvo_mlp& net, const unsigned char* image, const flo
   static bool cfg = false;
   if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
   ProfScope ps_(PK_BWD, st);
-  mlp_bwd_tc_kernel<<<grid, 160, smem, st>>>(a);
+  mlp_bwd_tc_kernel<<<grid, 352, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
   return 0;
 }

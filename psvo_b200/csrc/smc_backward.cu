@@ -63,18 +63,14 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
   const bool poisson = a.flags & PSVO_F_POISSON;
   MlpS<DXP, DYP> gs;
   MlpGradS<DXP, DYP> gg;
-  const bool ext = a.ext_mu != nullptr;      // MLP g forward / reverse run on tensor cores around this kernel
   float* p = smem;
   float* sg = p; p += 32;
   float* sstat = p; p += 32;
+  p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  float* gacc0 = p;
+  p = mlp_grad_carve<DXP, DYP>(a.g, p, gg);
+  for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
   float* stage = p;
-  if (!ext) {
-    p = mlp_stage<DXP, DYP>(a.g, p, gs);
-    float* gacc0 = p;
-    p = mlp_grad_carve<DXP, DYP>(a.g, p, gg);
-    for (float* q = gacc0 + threadIdx.x; q < p; q += blockDim.x) *q = 0.0f;
-    stage = p;
-  }
   if (threadIdx.x < 32) { sg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; sstat[threadIdx.x] = 0.0f; }
   __syncthreads();
 
@@ -96,12 +92,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
     float xx[1][DXP], mug[1][DYP];
 #pragma unroll
     for (int d = 0; d < DXP; ++d) xx[0][d] = x[d];
-    if (ext) {
-#pragma unroll
-      for (int d = 0; d < DYP; ++d) mug[0][d] = (live && d < Dy) ? a.ext_mu[((size_t)b * N + n) * Dy + d] : 0.0f;
-    } else {
-      mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
-    }
+    mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
     const float gl = particle_weight_grad(a, b, n, live);
     float G[DYP];
 #pragma unroll
@@ -118,13 +109,6 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
           st_sg[d] += gl * (z * z - 1.0f) / sg[d];
         }
       }
-    }
-    if (ext) {
-      if (live) {
-#pragma unroll
-        for (int d = 0; d < DYP; ++d) if (d < Dy) a.ext_g[((size_t)b * N + n) * Dy + d] = G[d];
-      }
-      continue;
     }
     float gx[DXP];
     mlp_bwd_tile<DXP, DYP>(gs, gg, x, G, gx, stage);
@@ -143,7 +127,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
   }
   __syncthreads();
   if (!poisson && threadIdx.x < Dy) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, sstat[threadIdx.x]);
-  if (!ext) mlp_grad_flush<DXP, DYP>(a.g, gg, a.gg);
+  mlp_grad_flush<DXP, DYP>(a.g, gg, a.gg);
 }
 
 template <int DXP>
@@ -161,9 +145,8 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
   float* C = p; p += 5 * DXP;                 // s1 | sf | sp | inv1 | inv2
   float* sred = p; p += 4 * 32;               // block partials: gm2 | gmu1 (t0) | gmuf (t0) | spare
   float* sstat = p; p += 4 * 32;              // SP | I1 | I2 | SF
-  const bool ext = a.ext_mu != nullptr && !t0;   // MLP q1 forward / reverse run on tensor cores around this kernel
   float* gacc0 = p;
-  if (!t0 && !ext) {
+  if (!t0) {
     p = mlp_stage<DXP, DXP>(a.q1, p, q1s);
     if (sep_f) p = mlp_stage<DXP, DXP>(a.f, p, fs);
     gacc0 = p;
@@ -202,13 +185,8 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
     if (!t0) {
 #pragma unroll
       for (int d = 0; d < DXP; ++d) par[0][d] = (live && d < Dx) ? a.X_anc[((bt - 1) * N + n) * Dx + d] : 0.0f;
-      if (ext) {
-#pragma unroll
-        for (int d = 0; d < DXP; ++d) mu1[0][d] = (live && d < Dx) ? a.ext_mu[bn * Dx + d] : 0.0f;
-      } else {
-        mlp_eval<DXP, DXP, 1>(q1s, par, mu1, nullptr, 0);
-        if (sep_f) mlp_eval<DXP, DXP, 1>(fs, par, muf, nullptr, 0);
-      }
+      mlp_eval<DXP, DXP, 1>(q1s, par, mu1, nullptr, 0);
+      if (sep_f) mlp_eval<DXP, DXP, 1>(fs, par, muf, nullptr, 0);
     } else {
 #pragma unroll
       for (int d = 0; d < DXP; ++d) {
@@ -276,12 +254,7 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
       }
     }
 
-    if (ext) {
-      if (live) {
-#pragma unroll
-        for (int d = 0; d < DXP; ++d) if (d < Dx) a.ext_g[bn * Dx + d] = gmu1[d];
-      }
-    } else if (!t0) {
+    if (!t0) {
       float ga[DXP], ga2[DXP];
       mlp_bwd_tile<DXP, DXP>(q1s, gq1, par[0], gmu1, ga, stage);
       if (sep_f) {
@@ -316,9 +289,119 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
     atomicAdd(a.stats + (ST_I2 * 2 + tau) * 32 + d, sstat[64 + d]);
     atomicAdd(a.stats + (ST_SF * 2 + tau) * 32 + d, sstat[96 + d]);
   }
-  if (!t0 && !ext) {
+  if (!t0) {
     mlp_grad_flush<DXP, DXP>(a.q1, gq1, a.gq1);
     if (sep_f) mlp_grad_flush<DXP, DXP>(a.f, gf, a.gf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Tensor-core path (default flags: use_bootstrap and use_2_q): the MLP forward (mu) and reverse (gx, dW, db) run in
+// tcgen05 kernels; these two light kernels do what is left of a step per particle -- the upstream gradient of the network
+// output, the sigma statistics and the per-sequence reductions -- with the same formulas as the fused kernels above.
+// ------------------------------------------------------------------------------------------------------
+// one thread per ELEMENT (row, d): fully coalesced reads of mu and writes of G
+__global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
+  __shared__ float sstat[32];
+  __shared__ float ssg[32];
+  const int Dy = a.Dy, N = a.N;
+  const bool poisson = a.flags & PSVO_F_POISSON;
+  if (threadIdx.x < 32) { sstat[threadIdx.x] = 0.0f; ssg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; }
+  __syncthreads();
+  const long long total = (long long)a.B * N * Dy;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / Dy;
+    const int d = (int)(e - row * Dy);
+    const int b = (int)(row / N), n = (int)(row - (long long)b * N);
+    const size_t bt = (size_t)b * a.T + a.t;
+    const float gl = particle_weight_grad(a, b, n, true);
+    const float y = __ldg(a.obs + bt * Dy + d);
+    const float mu = a.ext_mu[e];
+    if (poisson) {
+      const float z = y - (softplus(mu) + 1e-6f);
+      a.ext_g[e] = gl * z * sigmoidf(mu);
+    } else {
+      const float sg = ssg[d];
+      const float z = (y - mu) / sg;
+      a.ext_g[e] = gl * z / sg;
+      atomicAdd(&sstat[d], gl * (z * z - 1.0f) / sg);
+    }
+  }
+  __syncthreads();
+  if (!poisson && threadIdx.x < Dy) { const float v = sstat[threadIdx.x]; if (v != 0.0f) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, v); }
+}
+
+// t >= 1, f aliases d1 = q1:  mu1 = MLP q1(X_anc[t-1]) from ext_mu; writes d/dmu1 to ext_g
+__global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
+  __shared__ float sstat[4 * 32];
+  __shared__ float s1[PSVO_MAX_DX], sp[PSVO_MAX_DX], inv1[PSVO_MAX_DX], inv2[PSVO_MAX_DX];
+  const int Dx = a.Dx, N = a.N;
+  for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) sstat[i] = 0.0f;
+  if (threadIdx.x < PSVO_MAX_DX) {
+    const int d = threadIdx.x;
+    const float v1 = d < Dx ? __ldg(a.sig + SIG_Q1 * 32 + d) : 1.0f, v2 = d < Dx ? __ldg(a.sig + SIG_Q2 * 32 + d) : 1.0f;
+    s1[d] = v1; inv1[d] = 1.0f / v1; inv2[d] = 1.0f / v2; sp[d] = 1.0f / (1.0f / v1 + 1.0f / v2);
+  }
+  __syncthreads();
+  float st_sp[PSVO_MAX_DX], st_i1[PSVO_MAX_DX], st_i2[PSVO_MAX_DX], st_sf[PSVO_MAX_DX];
+#pragma unroll
+  for (int d = 0; d < PSVO_MAX_DX; ++d) st_sp[d] = st_i1[d] = st_i2[d] = st_sf[d] = 0.0f;
+  const long long rows = (long long)a.B * N;
+  const long long rows_pad = (rows + 31) / 32 * 32;                       // whole warps iterate together (shuffles below)
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < rows_pad; idx += (long long)gridDim.x * blockDim.x) {
+    const bool live = idx < rows;
+    const long long id = live ? idx : rows - 1;
+    const int b = (int)(id / N), n = (int)(id - (long long)b * N);
+    const size_t bt = (size_t)b * a.T + a.t;
+    const float gl = live ? particle_weight_grad(a, b, n, true) : 0.0f;
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool uniform = __all_sync(0xffffffffu, b == b0);                // the warp's particles belong to one sequence
+#pragma unroll
+    for (int d = 0; d < PSVO_MAX_DX; ++d) {
+      if (d < Dx) {
+        float gm2 = 0.0f;
+        if (live) {
+          const float mu1 = a.ext_mu[id * Dx + d];
+          const float X = a.Xs[(bt * N + n) * Dx + d];
+          const float m2 = __ldg(a.mu2_all + bt * Dx + d);
+          const float A = inv1[d] * mu1 + inv2[d] * m2;                   // m / sp
+          const float m = sp[d] * A;
+          const float e = (X - m) / sp[d];
+          const float zf = (X - mu1) / s1[d];                             // f_lp = d1_mvn.log_prob(X): sf = s1, muf = mu1
+          float gX = a.gXin[id * Dx + d] + a.gXg[id * Dx + d] - gl * zf / s1[d];
+          if (a.g_Xs != nullptr) gX += a.g_Xs[(bt * N + n) * Dx + d];
+          st_sp[d] += gX * e + gl / sp[d] + gX * A;
+          st_sf[d] += gl * (zf * zf - 1.0f) / s1[d];
+          st_i1[d] += gX * sp[d] * mu1;
+          st_i2[d] += gX * sp[d] * m2;
+          gm2 = gX * sp[d] * inv2[d];
+          a.ext_g[id * Dx + d] = gX * sp[d] * inv1[d] + gl * zf / s1[d];  // via m, plus d f_lp / d muf (muf IS mu1)
+        }
+        if (uniform) {
+          const float v = warp_sum(gm2);
+          if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(a.gmu2_all + bt * Dx + d, v);
+        } else if (live && gm2 != 0.0f) {
+          atomicAdd(a.gmu2_all + bt * Dx + d, gm2);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < PSVO_MAX_DX; ++d) {
+    if (d < Dx) {
+      float v = warp_sum(st_sp[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[d], v);
+      v = warp_sum(st_i1[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[32 + d], v);
+      v = warp_sum(st_i2[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[64 + d], v);
+      v = warp_sum(st_sf[d]); if ((threadIdx.x & 31) == 0) atomicAdd(&sstat[96 + d], v);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < Dx) {
+    const int d = threadIdx.x;
+    atomicAdd(a.stats + (ST_SP * 2 + 1) * 32 + d, sstat[d]);
+    atomicAdd(a.stats + (ST_I1 * 2 + 1) * 32 + d, sstat[32 + d]);
+    atomicAdd(a.stats + (ST_I2 * 2 + 1) * 32 + d, sstat[64 + d]);
+    atomicAdd(a.stats + (ST_SF * 2 + 1) * 32 + d, sstat[96 + d]);
   }
 }
 
@@ -397,15 +480,15 @@ static size_t staged_floats(const psvo_mlp& net, int din_pad, int dout_pad) {
 
 struct BwdWs {
   float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp;
-  float *tc_mu, *tc_g; unsigned char *img_g, *img_q1; unsigned int* gmax;     // tensor-core reverse mode (or NULL)
+  float *tc_mu, *tc_muq, *tc_g; unsigned char *img_g, *img_q1, *img_fwd; unsigned int* gmax;     // tensor-core reverse mode (or NULL)
   size_t bytes;
 };
 static bool tc_backward_ok(const psvo_dims* d, const psvo_params* p) {
   if (p == nullptr) return false;
   if (!(d->flags & PSVO_F_BOOTSTRAP) || !(d->flags & PSVO_F_TWO_Q)) return false;      // f aliases d1: one network per step side
   const long long rows = (long long)d->B * d->N;
-  return mlp_bwd_tc_supported(p->q1.net, rows) && mlp_bwd_tc_supported(p->g.net, rows) && tc_mlp_supported(p->q1.net) &&
-         tc_mlp_supported(p->g.net) && rows < (1LL << 31);
+  return mlp_bwd_tc_supported(p->q1.net, rows) && mlp_bwd_tc_supported(p->g.net, rows) &&
+         tc_pipeline_supported(p->q1.net, p->g.net, d->Dx, d->Dy) && rows < (1LL << 31);
 }
 static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
   BwdWs w;
@@ -418,10 +501,11 @@ static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
   w.gXa = take(BN * d->Dx); w.gXb = take(BN * d->Dx); w.gXg = take(BN * d->Dx);
   w.stats = take(ST_SLOTS * 2 * 32);
   w.gx0tmp = take((size_t)d->B * d->Dx0);
-  w.tc_mu = w.tc_g = nullptr; w.img_g = w.img_q1 = nullptr; w.gmax = nullptr;
+  w.tc_mu = w.tc_muq = w.tc_g = nullptr; w.img_g = w.img_q1 = w.img_fwd = nullptr; w.gmax = nullptr;
   if (tc_backward_ok(d, p)) {
     const size_t wide = d->Dx > d->Dy ? d->Dx : d->Dy;
-    w.tc_mu = take(BN * wide); w.tc_g = take(BN * wide);
+    w.tc_mu = take(BN * d->Dy); w.tc_muq = take(BN * d->Dx); w.tc_g = take(BN * wide);
+    w.img_fwd = reinterpret_cast<unsigned char*>(take(32 * 1024));
     w.img_g = reinterpret_cast<unsigned char*>(take(mlp_bwd_tc_image_bytes(p->g.net) / sizeof(float) + 64));
     w.img_q1 = reinterpret_cast<unsigned char*>(take(mlp_bwd_tc_image_bytes(p->q1.net) / sizeof(float) + 64));
     w.gmax = reinterpret_cast<unsigned int*>(take(64));
@@ -529,10 +613,13 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
     PSVO_CUDA(cudaMemsetAsync(w.img_q1, 0, mlp_bwd_tc_image_bytes(a.q1), st));
     if (int e = launch_mlp_bwd_tc_stage(a.g, w.img_g, st)) return e;
     if (int e = launch_mlp_bwd_tc_stage(a.q1, w.img_q1, st)) return e;
-    blkEx = blkPx = 256;                      // without their MLP part the kernels only need their constant blocks
-    smEx = 64 * sizeof(float); smPx = (5 * DXP + 256) * sizeof(float);
+    PropArgs ia;
+    ia.q1 = a.q1; ia.f = a.q1; ia.g = a.g; ia.Dx = Dx; ia.Dy = d->Dy;
+    if (int e = launch_tc_stage_image(ia, w.img_fwd, st)) return e;
+    (void)blkEx; (void)blkPx; (void)smEx; (void)smPx;
   }
   a.ext_mu = nullptr; a.ext_g = nullptr;
+  const int light_grid = (int)(((long long)B * N + 255) / 256 < 8LL * num_sms() ? ((long long)B * N + 255) / 256 : 8LL * num_sms());
 
   float* gXin = w.gXa;      // children contribution for the current step (zero at t = T-1)
   float* gXout = w.gXb;
@@ -544,24 +631,28 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
       const float* Xt = Xs + (size_t)t * N * Dx;
       int rc = 0;
       // ---- emission side
-      if ((rc = launch_particle_mlp_tc(a.g, Xt, sstr, B, N, w.tc_mu, st))) return rc;
+      {
+        Fwd2TcArgs fa;
+        fa.tc_image = w.img_fwd; fa.xq = t > 0 ? X_anc + (size_t)(t - 1) * N * Dx : nullptr; fa.xg = Xt; fa.x_seq_stride = sstr;
+        fa.muq = w.tc_muq; fa.mug = w.tc_mu; fa.B = B; fa.N = N; fa.Dx = Dx; fa.Dy = d->Dy; fa.H = a.g.width[0];
+        if ((rc = launch_tc_fwd2(fa, st))) return rc;
+      }
       a.ext_mu = w.tc_mu; a.ext_g = w.tc_g;
-      rc = -1;
-#define PSVO_CASE_EX(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkEx, grid_of(blkEx, smEx), smEx, st);
-      PSVO_CASE_EX(4, 4) PSVO_CASE_EX(4, 8) PSVO_CASE_EX(4, 16) PSVO_CASE_EX(4, 32)
-      PSVO_CASE_EX(8, 4) PSVO_CASE_EX(8, 8) PSVO_CASE_EX(8, 16) PSVO_CASE_EX(8, 32)
-      PSVO_CASE_EX(16, 4) PSVO_CASE_EX(16, 8) PSVO_CASE_EX(16, 16) PSVO_CASE_EX(16, 32)
-#undef PSVO_CASE_EX
-      if (rc) return rc;
+      {
+        ProfScope ps_(PK_BWD, st);
+        emission_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+        PSVO_LAUNCH_CHECK();
+      }
       if ((rc = launch_mlp_bwd_tc(a.g, w.img_g, Xt, sstr, w.tc_g, B, N, w.gXg, nullptr, 0, a.gg, w.gmax, st))) return rc;
       // ---- proposal side
       if (t > 0) {
         const float* Xp = X_anc + (size_t)(t - 1) * N * Dx;
-        if ((rc = launch_particle_mlp_tc(a.q1, Xp, sstr, B, N, w.tc_mu, st))) return rc;
-        rc = DXP == 4 ? launch_proposal_t<4>(a, blkPx, grid_of(blkPx, smPx), smPx, st)
-                      : (DXP == 8 ? launch_proposal_t<8>(a, blkPx, grid_of(blkPx, smPx), smPx, st)
-                                  : launch_proposal_t<16>(a, blkPx, grid_of(blkPx, smPx), smPx, st));
-        if (rc) return rc;
+        a.ext_mu = w.tc_muq;
+        {
+          ProfScope ps_(PK_BWD, st);
+          proposal_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+          PSVO_LAUNCH_CHECK();
+        }
         if ((rc = launch_mlp_bwd_tc(a.q1, w.img_q1, Xp, sstr, w.tc_g, B, N, gXout, anc + (size_t)(t - 1) * N, (long long)T * N,
                                     a.gq1, w.gmax, st))) return rc;
       } else {

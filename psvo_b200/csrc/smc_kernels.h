@@ -99,6 +99,17 @@ struct CandTcArgs {
 bool ffbsi_cand_tc_supported(const psvo_mlp& f, const psvo_mlp& g, int Dx, int Dy, long long rows);
 int launch_ffbsi_cand_tc(const CandTcArgs& a, cudaStream_t st);
 
+// tensor-core (tcgen05) forward of MLP q1 (on xq rows, optional) and MLP g (on xg rows) for the reverse pass
+// (smc_propagate_tc.cu); weight image from launch_tc_stage_image
+struct Fwd2TcArgs {
+  const unsigned char* tc_image;
+  const float* xq; const float* xg; long long x_seq_stride;     // row (b, n) at x + b*stride + n*Dx; xq may be NULL
+  float* muq; float* mug;                                       // (B*N, Dx) and (B*N, Dy)
+  int B, N, Dx, Dy, H;
+};
+int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st);
+bool tc_pipeline_supported(const psvo_mlp& q, const psvo_mlp& g, int Dx, int Dy);
+
 // tensor-core (tcgen05) reverse mode of a one-hidden-layer MLP over particle rows (mlp_bwd_tc.cu)
 bool mlp_bwd_tc_supported(const psvo_mlp& net, long long rows);
 size_t mlp_bwd_tc_image_bytes(const psvo_mlp& net);

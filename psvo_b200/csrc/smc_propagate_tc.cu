@@ -587,6 +587,131 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Plain forward of the two per-particle networks for the reverse pass (smc_backward.cu recomputes the network outputs
+// instead of storing them):  mu_q = MLP q1(xq rows), mu_g = MLP g(xg rows), same pipeline as smc_propagate_tc_kernel.
+// ------------------------------------------------------------------------------------------------------
+template <int NPG>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N, H = a.H;
+  const bool with_q = a.xq != nullptr;
+  const TcPropSmem L = tc_prop_layout(H, NPG);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nchunk = H / kTcChunk;
+  float* sb2q = reinterpret_cast<float*>(sm + L.b2q);
+  float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    const int n16 = (int)(L.consts / 16);
+#pragma unroll 4
+    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < 256) {
+    const uint32_t one2 = 0x3C003C00u;
+    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (warp == 0) tc::tmem_alloc(slot, 512);
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *slot;
+  const long long rows = (long long)a.B * N;
+  const int work = (int)((rows + 127) / 128);
+
+  TcNetDesc nq, ng;
+  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
+  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
+  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
+  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
+  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
+  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
+
+  if (warp >= kTcGroups * 4) {
+    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, with_q ? 0 : 1, nq, ng);
+  } else {
+    const int grp = warp >> 2;
+    TcGroup g;
+    const int gt = tid & 127;
+    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
+    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
+    for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+      const long long r = (long long)wi * 128 + gt;
+      const bool live = r < rows;
+      const int b = live ? (int)(r / N) : 0, n = live ? (int)(r - (long long)b * N) : 0;
+      float x[16];
+      if (with_q) {
+        const float* src = a.xq + (long long)b * a.x_seq_stride + (long long)n * Dx;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
+        tc_mlp_compute(g, x, nchunk);
+        float mu[16], mb[16];
+        tc::tmem_ld16(g.tD2, mu);
+        tc::tmem_ld16(g.tD2 + 16, mb);
+        if (live) {
+          float* dst = a.muq + r * Dx;
+#pragma unroll
+          for (int d = 0; d < 16; ++d) if (d < Dx) dst[d] = fmaf(mu[d] + mb[d], kWUnscale, sb2q[d]);
+        }
+      }
+      {
+        const float* src = a.xg + (long long)b * a.x_seq_stride + (long long)n * Dx;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
+        tc_mlp_compute(g, x, nchunk);
+#pragma unroll
+        for (int c0 = 0; c0 < NPG; c0 += 16) {
+          float mu[16], mb[16];
+          tc::tmem_ld16(g.tD2 + c0, mu);
+          tc::tmem_ld16(g.tD2 + NPG + c0, mb);
+          if (live) {
+            float* dst = a.mug + r * Dy;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (c0 + k < Dy) dst[c0 + k] = fmaf(mu[k] + mb[k], kWUnscale, sb2g[c0 + k]);
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st) {
+  PSVO_REQUIRE(a.tc_image != nullptr && a.xg != nullptr && a.mug != nullptr, "tensor-core forward: null buffer");
+  const TcPropSmem L = tc_prop_layout(a.H, 32);
+  const size_t smem = L.total + 128;
+  PSVO_REQUIRE(smem <= 227 * 1024, "tensor-core forward: %zu B of shared memory", smem);
+  const long long tiles = ((long long)a.B * a.N + 127) / 128;
+  long long grid = (tiles + kTcGroups - 1) / kTcGroups;
+  if (grid > num_sms()) grid = num_sms();
+  static bool cfg = false;
+  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(tc_fwd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+  ProfScope ps_(PK_BWD, st);
+  tc_fwd2_kernel<32><<<(int)grid, kTcThreads, smem, st>>>(a);
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+// shapes the forward tensor-core pipeline handles (one hidden layer of 32..256 units in both networks)
+bool tc_pipeline_supported(const psvo_mlp& q, const psvo_mlp& g, int Dx, int Dy) {
+  if (q.n_hidden != 1 || g.n_hidden != 1) return false;
+  const int H = g.width[0];
+  return q.width[0] == H && H >= 32 && H <= 256 && (H % 32) == 0 && Dx <= 16 && Dy <= 32;
+}
+
 bool ffbsi_cand_tc_supported(const psvo_mlp& f, const psvo_mlp& g, int Dx, int Dy, long long rows) {
   static const bool disabled = getenv("PSVO_DISABLE_TC") != nullptr && getenv("PSVO_DISABLE_TC")[0] == '1';
   if (disabled) return false;
