@@ -50,6 +50,9 @@ WORKLOADS = {
     # forward filter + FFBSi + reverse mode + Adam per sequence, through psvo_b200.trainer-style calls
     "c1_psvo_train": dict(cls="PSVO", Dx=2, Dy=1, H=[32], N=16, M=16, T=200, B=1, train=True, n_seq=200,
                           note="notebooks/PSVO.ipynb training run shape: PSVO, Dx=2, Dy=1, N=16, M=16, T=200, batch 1, 200 sequences/epoch"),
+    # forward filter + reverse mode (psvo_smc_forward + psvo_smc_backward) at the config-5 shard shape, T shortened
+    "c5_fwd_bwd": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=4096, T=50, B=128, fwd_bwd=True,
+                       note="BASELINE configs[4] shard shape (N=4096, Dx=16, Dy=32, H=256, B=128 per GPU), T=50: forward + reverse mode"),
     "tiny": dict(cls="AESMC", Dx=16, Dy=32, H=[256], N=512, T=20, B=8, note="smoke-size config-5 shape"),
 }
 
@@ -390,6 +393,60 @@ def run_train_epoch(args, w, local_rank):
             "log_ZSMC_first_last": [first, lastv]}
 
 
+def run_fwd_bwd(args, w, local_rank):
+    """particle-steps/s of one objective evaluation WITH its gradient (forward filter + reverse mode), device-timed."""
+    import ctypes as C
+    from psvo_b200 import _lib, ops, functional as Fn
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.AESMC import AESMC
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    FLAGS = make_flags(w)
+    torch.manual_seed(1234)
+    model = SSM(FLAGS).to(dev)
+    smc = AESMC(model, FLAGS)
+    obs = synth_obs(w, w["B"], 1234, 0).to(dev)
+    smc._build_nets(w["Dy"], w["Dy"], dev)
+
+    def step(seed):
+        for p in model.parameters():
+            p.grad = None
+        z, _ = smc.get_log_ZSMC(obs, None, seed=seed)
+        (-z).backward()
+        return z
+    for i in range(max(2, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fwd_ms = bwd_ms = 0.0
+    for i in range(args.steps):
+        for p in model.parameters():
+            p.grad = None
+        ev[0].record()
+        z, _ = smc.get_log_ZSMC(obs, None, seed=100 + i)
+        ev[1].record()
+        (-z).backward()
+        ev[2].record()
+        torch.cuda.synchronize()
+        fwd_ms += ev[0].elapsed_time(ev[1]); bwd_ms += ev[1].elapsed_time(ev[2])
+    fwd_ms /= args.steps; bwd_ms /= args.steps
+    lib.psvo_profile_enable(1)
+    step(999)
+    torch.cuda.synchronize()
+    kms, kl = (C.c_double * 8)(), (C.c_int64 * 8)()
+    lib.psvo_profile_read(kms, kl)
+    lib.psvo_profile_enable(0)
+    psteps = w["B"] * w["T"] * w["N"]
+    return {"metric": "particle-steps/sec (SMC forward filter + reverse mode)", "value": psteps / ((fwd_ms + bwd_ms) * 1e-3),
+            "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(2, args.warmup),
+            "ms_per_step": fwd_ms + bwd_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, "note": w["note"]},
+            "forward_ms": fwd_ms, "backward_ms": bwd_ms, "backward_over_forward": bwd_ms / fwd_ms,
+            "kernel_ms": {"forward (propagate+resample)": kms[0] + kms[1], "reverse mode (PK_BWD)": kms[4], "row MLPs": kms[2]},
+            "log_ZSMC": float(z.detach())}
+
+
 def cpu_sample(w, budget_s=15.0, threads=None):
     """Time the oracle restatement (PyTorch CPU fp32) on a bounded slice of the workload."""
     from oracle import psvo_oracle as O
@@ -475,6 +532,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if w.get("fwd_bwd"):
+            print(json.dumps(run_fwd_bwd(args, w, local_rank)), flush=True)
+            return
         if w.get("train"):
             print(json.dumps(run_train_epoch(args, w, local_rank)), flush=True)
             return
