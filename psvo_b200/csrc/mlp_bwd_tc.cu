@@ -244,34 +244,52 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
       const long long r = (long long)tile * 128 + row;
       const bool live = r < rows;
       const int b = live ? (int)(r / N) : 0, n = live ? (int)(r - (long long)b * N) : 0;
-      // the previous tile's MMAs still read x / G (weight gradients of its last two chunks): wait for them
+      // this thread's half of the tile's rows: x (half 0) or G (half 1), loaded into registers BEFORE waiting for the
+      // previous tile's MMAs (they still read the x / G operands), so the global-load latency hides behind that drain
+      float rv[32];
+      {
+        const float* src = half == 0 ? a.x + (long long)b * a.x_seq_stride + (long long)n * din : a.g + r * dout;
+        const int w = half == 0 ? din : dout;
+        if (live && (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < w) v4 = __ldg(reinterpret_cast<const float4*>(src) + q);
+            rv[4 * q] = v4.x; rv[4 * q + 1] = v4.y; rv[4 * q + 2] = v4.z; rv[4 * q + 3] = v4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rv[i] = (live && i < w) ? __ldg(src + i) : 0.0f;
+        }
+      }
       if (n_tile > 0) { wait_all_mmas(n_chunk); }
       if (half == 0) {
-        const float* xr = a.x + (long long)b * a.x_seq_stride + (long long)n * din;
 #pragma unroll
         for (int kg = 0; kg < 2; ++kg) {
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (live && kg * 8 + i < din) ? xr[kg * 8 + i] : 0.0f;
+          for (int i = 0; i < 8; ++i) v[i] = rv[kg * 8 + i];
           uint4 hi, lo;
           tc::split8_f16(v, hi, lo);
           *reinterpret_cast<uint4*>(px_h + kg * kBtGrp) = hi; *reinterpret_cast<uint4*>(px_l + kg * kBtGrp) = lo;
         }
       } else {
-        const float* gr = a.g + r * dout;
-        for (int kg = 0; kg < NP / 8; ++kg) {
-          float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int o = kg * 8 + i;
-            const float gv = (live && o < dout) ? gr[o] : 0.0f;
-            v[i] = gv * sG;
-            const float s = warp_sum(gv);                                 // db2 = sum over rows of G
-            if (lane == 0 && o < dout && s != 0.0f) atomicAdd(&sdb2[o], s);
+        for (int kg = 0; kg < 4; ++kg) {
+          if (kg < NP / 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int o = kg * 8 + i;
+              const float gv = rv[o];
+              v[i] = gv * sG;
+              const float s = warp_sum(gv);                                 // db2 = sum over rows of G
+              if (lane == 0 && o < dout && s != 0.0f) atomicAdd(&sdb2[o], s);
+            }
+            uint4 hi, lo;
+            tc::split8_f16(v, hi, lo);
+            *reinterpret_cast<uint4*>(pg_h + kg * kBtGrp) = hi; *reinterpret_cast<uint4*>(pg_l + kg * kBtGrp) = lo;
           }
-          uint4 hi, lo;
-          tc::split8_f16(v, hi, lo);
-          *reinterpret_cast<uint4*>(pg_h + kg * kBtGrp) = hi; *reinterpret_cast<uint4*>(pg_l + kg * kBtGrp) = lo;
         }
       }
       tc::fence_proxy_async();

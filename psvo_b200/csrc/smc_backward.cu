@@ -309,6 +309,8 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
   if (threadIdx.x < 32) { sstat[threadIdx.x] = 0.0f; ssg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; }
   __syncthreads();
   const long long total = (long long)a.B * N * Dy;
+  const bool fixed_d = (blockDim.x % Dy) == 0;        // then e % Dy is the same in every iteration of a thread
+  float acc = 0.0f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long row = e / Dy;
     const int d = (int)(e - row * Dy);
@@ -324,9 +326,11 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
       const float sg = ssg[d];
       const float z = (y - mu) / sg;
       a.ext_g[e] = gl * z / sg;
-      atomicAdd(&sstat[d], gl * (z * z - 1.0f) / sg);
+      const float st = gl * (z * z - 1.0f) / sg;
+      if (fixed_d) acc += st; else atomicAdd(&sstat[d], st);
     }
   }
+  if (!poisson && fixed_d && acc != 0.0f) atomicAdd(&sstat[threadIdx.x % Dy], acc);
   __syncthreads();
   if (!poisson && threadIdx.x < Dy) { const float v = sstat[threadIdx.x]; if (v != 0.0f) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, v); }
 }
@@ -356,19 +360,41 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
     const float gl = live ? particle_weight_grad(a, b, n, true) : 0.0f;
     const int b0 = __shfl_sync(0xffffffffu, b, 0);
     const bool uniform = __all_sync(0xffffffffu, b == b0);                // the warp's particles belong to one sequence
+    // the row's four inputs in registers first (128-bit loads when Dx is a multiple of 4): one latency instead of 4*Dx
+    float r_mu[PSVO_MAX_DX], r_x[PSVO_MAX_DX], r_gi[PSVO_MAX_DX], r_gg[PSVO_MAX_DX];
+    {
+      const float* p_mu = a.ext_mu + id * Dx; const float* p_x = a.Xs + (bt * N + n) * Dx;
+      const float* p_gi = a.gXin + id * Dx;   const float* p_gg = a.gXg + id * Dx;
+      if ((Dx & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < PSVO_MAX_DX / 4; ++q) {
+          if (4 * q < Dx) {
+            const float4 v0 = *reinterpret_cast<const float4*>(p_mu + 4 * q), v1 = *reinterpret_cast<const float4*>(p_x + 4 * q);
+            const float4 v2 = *reinterpret_cast<const float4*>(p_gi + 4 * q), v3 = *reinterpret_cast<const float4*>(p_gg + 4 * q);
+            r_mu[4 * q] = v0.x; r_mu[4 * q + 1] = v0.y; r_mu[4 * q + 2] = v0.z; r_mu[4 * q + 3] = v0.w;
+            r_x[4 * q] = v1.x; r_x[4 * q + 1] = v1.y; r_x[4 * q + 2] = v1.z; r_x[4 * q + 3] = v1.w;
+            r_gi[4 * q] = v2.x; r_gi[4 * q + 1] = v2.y; r_gi[4 * q + 2] = v2.z; r_gi[4 * q + 3] = v2.w;
+            r_gg[4 * q] = v3.x; r_gg[4 * q + 1] = v3.y; r_gg[4 * q + 2] = v3.z; r_gg[4 * q + 3] = v3.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < PSVO_MAX_DX; ++d) if (d < Dx) { r_mu[d] = p_mu[d]; r_x[d] = p_x[d]; r_gi[d] = p_gi[d]; r_gg[d] = p_gg[d]; }
+      }
+    }
 #pragma unroll
     for (int d = 0; d < PSVO_MAX_DX; ++d) {
       if (d < Dx) {
         float gm2 = 0.0f;
         if (live) {
-          const float mu1 = a.ext_mu[id * Dx + d];
-          const float X = a.Xs[(bt * N + n) * Dx + d];
+          const float mu1 = r_mu[d];
+          const float X = r_x[d];
           const float m2 = __ldg(a.mu2_all + bt * Dx + d);
           const float A = inv1[d] * mu1 + inv2[d] * m2;                   // m / sp
           const float m = sp[d] * A;
           const float e = (X - m) / sp[d];
           const float zf = (X - mu1) / s1[d];                             // f_lp = d1_mvn.log_prob(X): sf = s1, muf = mu1
-          float gX = a.gXin[id * Dx + d] + a.gXg[id * Dx + d] - gl * zf / s1[d];
+          float gX = r_gi[d] + r_gg[d] - gl * zf / s1[d];
           if (a.g_Xs != nullptr) gX += a.g_Xs[(bt * N + n) * Dx + d];
           st_sp[d] += gX * e + gl / sp[d] + gX * A;
           st_sf[d] += gl * (zf * zf - 1.0f) / s1[d];
@@ -607,7 +633,6 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   // per-particle networks run as  tcgen05 forward (mu) -> this file's kernels without their MLP part (upstream gradient,
   // sigma statistics, per-sequence reductions) -> tcgen05 reverse (mlp_bwd_tc.cu: gx, dW, db)
   const bool tc = w.tc_mu != nullptr;
-  int blkEx = 0, blkPx = 0; size_t smEx = 0, smPx = 0;
   if (tc) {
     PSVO_CUDA(cudaMemsetAsync(w.img_g, 0, mlp_bwd_tc_image_bytes(a.g), st));
     PSVO_CUDA(cudaMemsetAsync(w.img_q1, 0, mlp_bwd_tc_image_bytes(a.q1), st));
@@ -616,7 +641,6 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
     PropArgs ia;
     ia.q1 = a.q1; ia.f = a.q1; ia.g = a.g; ia.Dx = Dx; ia.Dy = d->Dy;
     if (int e = launch_tc_stage_image(ia, w.img_fwd, st)) return e;
-    (void)blkEx; (void)blkPx; (void)smEx; (void)smPx;
   }
   a.ext_mu = nullptr; a.ext_g = nullptr;
   const int light_grid = (int)(((long long)B * N + 255) / 256 < 8LL * num_sms() ? ((long long)B * N + 255) / 256 : 8LL * num_sms());
