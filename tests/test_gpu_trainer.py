@@ -38,3 +38,24 @@ def test_train_on_fhn_slice(cls_name, tmp_path):
     assert R2.shape == (6,) and np.isfinite(R2).all()
     assert log["Xs"].shape[1:] == (T, 32, 2)
     assert os.path.exists(os.path.join(str(tmp_path), "history.json")) and os.path.exists(os.path.join(str(tmp_path), "metric_1.p"))
+
+
+def test_runner_main_on_fhn_slice(tmp_path):
+    """psvo_b200.runner: flags -> load_data -> SSM -> objective -> trainer -> param.json / history.json / data.p"""
+    import json
+    import pickle
+    from psvo_b200 import runner
+    F = runner.parse_flags(["--datadir", os.path.join(HERE, "golden"), "--datadict", "fhn_slice.p", "--Dx", "2", "--n_particles", "16",
+                            "--n_particles_for_BSim_proposal", "4", "--batch_size", "3", "--epoch", "2", "--MSE_steps", "3",
+                            "--rslt_dir_name", str(tmp_path), "--saving_num", "2", "--PSVO", "False", "--AESMC", "True"])
+    assert F.AESMC and not F.PSVO and F.lr == pytest.approx(3e-3)
+    history, rlt_dir = runner.main(F)
+    assert F.time == 200 and F.n_train == 6 and F.n_test == 3
+    assert len(history["log_ZSMC_trains"]) == 3 and all(np.isfinite(history["log_ZSMC_trains"]))
+    with open(os.path.join(rlt_dir, "param.json")) as f:
+        assert json.load(f)["n_particles"] == 16
+    with open(os.path.join(rlt_dir, "data.p"), "rb") as f:
+        d = pickle.load(f)
+    assert d["learned_model_dict"]["Xs_val"].shape == (2, 200, 16, 2) and len(d["learned_model_dict"]["y_hat_val"]) == 4
+    with pytest.raises(ValueError):
+        runner.objective_class(runner.parse_flags(["--PSVO", "True", "--SVO", "True"]))
