@@ -27,6 +27,7 @@ CASES = [
     ("c5_shape_tensor_core", 16, 32, 32, 32, [256], 4096, 2, 3, O.Flags()),
     ("tensor_core_ragged", 5, 7, 6, 9, [128], 3000, 3, 3, O.Flags()),
     ("tensor_core_poisson_h64", 4, 1, 8, 8, [64], 2100, 4, 3, O.Flags(poisson_emission=True)),
+    ("tensor_core_iwae", 4, 2, 4, 4, [64], 2100, 4, 3, O.Flags(resample_particles=False)),
 ]
 
 
@@ -124,6 +125,9 @@ SMOOTH_CASES = [
     ("psvowr_no2q", 2, 2, 4, [8], 32, 4, 2, 4, True, O.Flags(use_2_q=False)),
     ("psvo_c5_shape", 16, 32, 16, [64], 32, 4, 1, 3, False, O.Flags()),
     ("psvo_T2", 2, 1, 4, [8], 16, 4, 2, 2, False, O.Flags()),
+    # >= 8192 filter particles per step and H = 64: the filter part of the reverse pass runs on tensor cores and receives
+    # g_Xs / g_log_Ws from psvo_ffbsi_backward
+    ("psvo_filter_tensor_core", 4, 3, 8, [64], 1056, 2, 8, 3, False, O.Flags()),
 ]
 
 
