@@ -41,6 +41,9 @@ extern "C" {
 #define PSVO_F_RESAMPLE 4u        /* self.resample_particles (SVO.py:27; IWAE.py:11 clears it) */
 #define PSVO_F_POISSON 8u         /* FLAGS.poisson_emission : tf_poisson emission (src/model.py:153-160) */
 #define PSVO_F_WITH_RESAMPLING 16u/* PSVOwR variant of the backward simulation (src/SMC/PSVOwR.py) */
+#define PSVO_F_SYSTEMATIC 32u     /* EXTRA, not in the reference (it only has multinomial, src/SMC/SVO.py:266-300): systematic
+                                     resampling in the forward filter -- child n uses u_n = (n + u_0) / N with the single
+                                     draw u_0 = u[b][t][0] (or its Philox value); same fixed-point CDF and search */
 
 typedef void* psvo_stream_t;      /* cudaStream_t */
 

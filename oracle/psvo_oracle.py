@@ -200,6 +200,18 @@ def resample_idx(logits, u) -> np.ndarray:
     return np.minimum(out, K - 1).reshape(lead + (u.shape[-1],))
 
 
+def resample_idx_systematic(logits, u0) -> np.ndarray:
+    """EXTRA (the reference has no systematic resampling): child n of every row uses u_n = (n + u0) / K with the row's single
+    draw u0, quantised like the multinomial rule: u24_n = floor((n 2^24 + floor(u0 2^24)) / K).  logits (..., K), u0 (...)."""
+    logits = np.asarray(logits.detach().cpu().numpy() if isinstance(logits, torch.Tensor) else logits, dtype=np.float32)
+    u0 = np.asarray(u0.detach().cpu().numpy() if isinstance(u0, torch.Tensor) else u0, dtype=np.float32)
+    K = logits.shape[-1]
+    u24 = (u0 * np.float32(16777216.0)).astype(np.float32).astype(np.uint64)[..., None]
+    n = np.arange(K, dtype=np.uint64)
+    u24n = ((n << np.uint64(24)) + u24) // np.uint64(K)
+    return resample_idx(logits, (u24n.astype(np.float64) / 16777216.0).astype(np.float32))
+
+
 # --------------------------------------------------------------------------------------
 # forward filter (src/SMC/SVO.py:60-180) and log_ZSMC (SVO.py:302-311)
 # --------------------------------------------------------------------------------------

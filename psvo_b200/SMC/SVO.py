@@ -24,6 +24,9 @@ class SVO:
         self.use_stack_rnn = FLAGS.use_stack_rnn
         self.smooth_obs = True
         self.resample_particles = True
+        # EXTRA (not in the reference, which only has multinomial resampling): FLAGS.systematic_resampling=True switches the
+        # forward filter to systematic resampling (lower-variance ancestry; the objective stays a valid SMC bound)
+        self.systematic_resampling = bool(getattr(FLAGS, "systematic_resampling", False))
         self.name = name
         self.seed = int(getattr(FLAGS, "seed", 0))
         self._calls = 0
@@ -63,7 +66,7 @@ class SVO:
             seed = (self.seed << 20) + self._calls
             self._calls += 1
         flags = Fn.flag_bits(self.model.use_bootstrap, self.model.use_2_q, self.resample_particles,
-                             self.model.poisson_emission)
+                             self.model.poisson_emission, systematic=self.systematic_resampling)
         P = self.model.dist_params()
         return ops.smc_filter(P, flags, obs, pre_obs, pre_X0, self.n_particles, eps=eps, u=u, forced_anc=forced,
                               seed=seed, seq_offset=self.seq_offset, out=out)

@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpsvo_b200.so")
 
 MAX_HIDDEN = 4
-F_BOOTSTRAP, F_TWO_Q, F_RESAMPLE, F_POISSON, F_WITH_RESAMPLING = 1, 2, 4, 8, 16
+F_BOOTSTRAP, F_TWO_Q, F_RESAMPLE, F_POISSON, F_WITH_RESAMPLING, F_SYSTEMATIC = 1, 2, 4, 8, 16, 32
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
 

@@ -402,12 +402,15 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
           const int f = a.forced_anc[bt * N + n];
           anc[k] = f < 0 ? 0 : (f >= N ? N - 1 : f);
         } else {
+          const bool systematic = a.flags & PSVO_F_SYSTEMATIC;
+          const int nu = systematic ? 0 : n;                          // systematic: one draw per (b, t), particle 0's
           uint32_t u24;
-          if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + n]);
+          if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + nu]);
           else {
-            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + n;
+            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + nu;
             u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
           }
+          if (systematic) u24 = (uint32_t)((((uint64_t)n << 24) + u24) / (uint64_t)N);   // floor(2^24 (n + u_0) / N)
           thr[k] = draw_threshold(total, u24);
           search[k] = true;
         }

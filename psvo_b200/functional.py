@@ -93,10 +93,10 @@ def make_dims(N, B, T, Dx, Dy, Dobs, Dx0, flags, M=0, Dfeat=0, seq_offset=0):
     return d
 
 
-def flag_bits(use_bootstrap=True, use_2_q=True, resample=True, poisson=False, with_resampling=False):
+def flag_bits(use_bootstrap=True, use_2_q=True, resample=True, poisson=False, with_resampling=False, systematic=False):
     return (L.F_BOOTSTRAP if use_bootstrap else 0) | (L.F_TWO_Q if use_2_q else 0) | \
         (L.F_RESAMPLE if resample else 0) | (L.F_POISSON if poisson else 0) | \
-        (L.F_WITH_RESAMPLING if with_resampling else 0)
+        (L.F_WITH_RESAMPLING if with_resampling else 0) | (L.F_SYSTEMATIC if systematic else 0)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -270,3 +270,25 @@ def test_per_step_kernels_when_persistent_path_is_disabled():
                         "-k", "forward_filter or philox_mode or sharded or kalman"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_systematic_resampling_extra():
+    """EXTRA flag PSVO_F_SYSTEMATIC (no reference counterpart): ancestors follow the oracle's systematic rule bit for bit, are
+    non-decreasing in n, every particle gets floor/ceil of N * w copies, and the estimator stays close to multinomial's."""
+    name, Dx, Dy, Dobs, Dx0, hidden, N, B, T, F = CONFIGS[1]
+    N = 500
+    P, obs, pre_obs, pre_x0, eps, u = make_case(Dx, Dy, Dobs, Dx0, hidden, N, B, T, F)
+    f = Fn()
+    Pd = to_dev(P)
+    fl = f.flag_bits(F.use_bootstrap, F.use_2_q, True, F.poisson_emission, systematic=True)
+    r = f.smc_forward_raw(Pd, fl, obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N, eps=eps.to(DEV), u=u.to(DEV))
+    anc = r["anc"].cpu().numpy()
+    lw = r["log_Ws"].cpu().numpy()
+    want = O.resample_idx_systematic(lw.reshape(B * T, N), u[:, :, 0].numpy().reshape(B * T)).reshape(B, T, N)
+    assert (anc == want).all()
+    assert (np.diff(anc, axis=-1) >= 0).all()
+    w = torch.softmax(r["log_Ws"].double(), -1).cpu().numpy()
+    counts = np.stack([[np.bincount(anc[b, t], minlength=N) for t in range(T)] for b in range(B)])
+    assert (np.abs(counts - N * w) < 1.0 + 1e-6).all()
+    m = f.smc_forward_raw(Pd, flags_of(F), obs.to(DEV), pre_obs.to(DEV), pre_x0.to(DEV), N, eps=eps.to(DEV), u=u.to(DEV))
+    assert torch.isfinite(r["logZ_b"]).all() and float((r["logZ_b"] - m["logZ_b"]).abs().max()) < 0.05 * float(m["logZ_b"].abs().max())
