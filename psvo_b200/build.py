@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "lib", "libpsvo_b200.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-              "-Xptxas", "-v"]
+              "-Xptxas", "-v"] + (["-DPSVO_TC_TRACE"] if os.environ.get("PSVO_TC_TRACE") == "1" else [])
 
 
 def _nvcc():

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
 
   if (warp == kPtGroups * 4 + 2) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t q = 0;
       for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
         const int b = wi / items_per_seq;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs
     __syncwarp();
   } else if (warp >= kPtGroups * 4) {
     // ================================ MMA issuers: warp 16 serves groups 0-1, warp 17 groups 2-3 ================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const int g0 = (warp - kPtGroups * 4) * 2;
       const uint32_t idesc = tc::make_idesc_f16(128, kPtCols);
       uint64_t adesc_hi[2], adesc_lo[2];

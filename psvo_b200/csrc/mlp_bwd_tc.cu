@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
     // per chunk), so three warps issue side by side, each owning its accumulators:
     //   warp 8: row-wise products L1 / dh / dx      warp 9: dW2_c = h_c^T G      warp 10: dW1_c = gpre_c^T [x | 1]
     // a_free counts one commit per warp.
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t id_row64 = tc::make_idesc_f16(128, 64);
       const uint32_t id_dx = tc::make_idesc_f16(128, 16) | (1u << 16);      // B = W1 (the L1 operand) read MN-major: (d, j)
       const uint32_t id_w2 = tc::make_idesc_f16(64, NP) | (1u << 15) | (1u << 16);

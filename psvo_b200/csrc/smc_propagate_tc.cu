@@ -30,6 +30,23 @@
 
 namespace psvo {
 
+#ifdef PSVO_TC_TRACE
+// low-overhead timeline of CTA 0: thread 0 (compute group 0) and thread 512 (its MMA warp); the last launch wins
+__device__ long long* g_tc_trace = nullptr;
+__shared__ int s_tc_trace_n[2];
+#define TC_TRACE_INIT() do { if (threadIdx.x < 2) s_tc_trace_n[threadIdx.x] = 0; } while (0)
+#define TC_TRACE(tag) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 512)) { \
+    long long* tb_ = g_tc_trace; const int w_ = threadIdx.x == 512; const int i_ = s_tc_trace_n[w_]; \
+    if (tb_ != nullptr && (unsigned)i_ < 4096u) { s_tc_trace_n[w_] = i_ + 1; tb_[2 * (w_ * 4096 + i_)] = (tag) + w_ * 100; tb_[2 * (w_ * 4096 + i_) + 1] = clock64(); } } } while (0)
+extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_trace(long long* buf) {
+  cudaMemcpyToSymbol(g_tc_trace, &buf, sizeof(buf));
+  return 0;
+}
+#else
+#define TC_TRACE(tag) do { } while (0)
+#define TC_TRACE_INIT() do { } while (0)
+#endif
+
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
@@ -43,6 +60,7 @@ struct TcPropSmem {
   uint32_t a_ones;                                     // its A operand [128 x K=16]: k=0,1 = 1 (same for every row)
   uint32_t b1q, b2q, b1g, b2g, consts;                                        // fp32
   uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups], a2_hi[kTcGroups], a2_lo[kTcGroups];
+  uint32_t rowc;                                       // per group, two tile parities: [mu2 (16) | obs (32) | pad] fp32
   uint32_t bars, slot, total;
 };
 
@@ -62,6 +80,7 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
     s.a2_hi[g] = PSVO_TAKE(128 * kTcChunk * 2); s.a2_lo[g] = PSVO_TAKE(128 * kTcChunk * 2);
   }
   s.a_ones = PSVO_TAKE(128 * 16 * 2);
+  s.rowc = PSVO_TAKE(kTcGroups * 2 * 64 * 4);
   s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full, mD1[0], mD1[1], mL2
 #undef PSVO_TAKE
   s.total = o;
@@ -89,19 +108,24 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
 // hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> scale + bias -> ReLU -> fp16 hi/lo -> A2 -> arrive
 template <int BUF>
 __device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
+  TC_TRACE(1);
   tc_wait<BUF>(g.mD1 + BUF, g.par);                                       // L1(c) complete
   tc::fence_after_sync();
+  TC_TRACE(2);
   float v[32];
   tc::tmem_ld32(g.tD1 + BUF * 32, v);
+  TC_TRACE(3);
   uint4 hi[4], lo[4];
 #pragma unroll
   for (int kg = 0; kg < 4; ++kg) {
     float h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = fmaxf(v[kg * 8 + i], 0.f);          // D1 = 16 (W1^T x + b1): the bias rode in the MMA
-    tc::split8_f16_trunc(h, hi[kg], lo[kg]);
+    for (int i = 0; i < 8; ++i) h[i] = v[kg * 8 + i];                      // D1 = 16 (W1^T x + b1): the bias rode in the MMA
+    tc::split8_relu_f16(h, hi[kg], lo[kg]);                                // ReLU inside the packing conversion
   }
+  TC_TRACE(4);
   if (c > 0) tc_wait<2>(g.mL2, g.par);                                     // L2(c-1) complete -> A2 reusable
+  TC_TRACE(5);
 #pragma unroll
   for (int kg = 0; kg < 4; ++kg) {
     *reinterpret_cast<uint4*>(g.pa2h + kg * 2048) = hi[kg];
@@ -110,6 +134,7 @@ __device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
   tc::fence_proxy_async();
   tc::fence_before_sync();
   tc::mbar_arrive(g.full);                                                 // A2(c) staged, D1[BUF] released
+  TC_TRACE(6);
 }
 
 // compute-group side of one network: x = this thread's input row.  On return the accumulator D2 (2*NP columns:
@@ -174,17 +199,21 @@ __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem&
     for (int net = first_net; net < 2; ++net) {
       const TcNetDesc& nd = net ? ng : nq;
       for (int s2 = 0; s2 <= nchunk; ++s2) {
+        TC_TRACE(10);
         tc::mbar_wait(full, phase); phase ^= 1;
         tc::fence_after_sync();
-        if (lane == 0) {
+        TC_TRACE(11);
+        if (tc::elect_one()) {
           if (s2 == 0) {
             tc_issue_l1(nd, a1h, a1l, aones, tD1, 0, mD1);
             if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, aones, tD1, 1, mD1);
           } else {
             tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
+            TC_TRACE(13);
             if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, aones, tD1, s2 + 1, mD1);
           }
         }
+        TC_TRACE(12);
         __syncwarp();
       }
     }
@@ -259,6 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
     *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
+  TC_TRACE_INIT();
   if (warp == 0) tc::tmem_alloc(slot, 512);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -304,6 +334,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
 
+    uint32_t tile_it = 0;
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const int b = wi / tiles_per_seq;
       const int n = (wi - b * tiles_per_seq) * 128 + gt;
@@ -311,6 +342,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       const size_t bt = (size_t)b * a.T + a.t;
       const size_t row = bt * N + (live ? n : 0);
 
+      TC_TRACE(20);
+      // ---- per-sequence rows every particle of the tile shares (second proposal mean, observation): one global load
+      //      per thread into the group's double-buffered slot instead of 48 dependent broadcast loads per thread
+      const float* rc = reinterpret_cast<const float*>(sm + L.rowc) + (grp * 2 + (tile_it & 1)) * 64;
+      {
+        float* rcw = const_cast<float*>(rc);
+        if (two_q && gt < Dx) rcw[gt] = __ldg(a.mu2_all + bt * Dx + gt);
+        if (gt >= 32 && gt < 32 + Dy) rcw[16 + gt - 32] = __ldg(a.obs + bt * Dy + gt - 32);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      ++tile_it;
       float x[16], mu1[16];
       // ---- d1 mean: MLP q1 on the resampled parent (t >= 1) or the per-sequence q0 mean (t = 0)
       if (!t0) {
@@ -358,7 +400,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       for (int d = 0; d < 16; ++d) {
         float m = mu1[d];
         if (two_q) {
-          const float m2 = d < Dx ? __ldg(a.mu2_all + bt * Dx + d) : 0.0f;
+          const float m2 = d < Dx ? rc[d] : 0.0f;
           m = sp[d] * (inv1[d] * mu1[d] + inv2[d] * m2);
         }
         const float X = fmaf(sp[d], e[d], m);
@@ -380,8 +422,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         }
       }
 
+      TC_TRACE(21);
       // ---- emission
       tc_mlp_compute(g, x, nchunk);
+      TC_TRACE(22);
       float gsum = 0.f;
 #pragma unroll
       for (int c = 0; c < NPG; c += 16) {
@@ -392,7 +436,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         for (int i = 0; i < 16; ++i) {
           const int d = c + i;
           if (d < Dy) {
-            const float y = __ldg(a.obs + bt * Dy + d);
+            const float y = rc[16 + d];
             const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
             const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
@@ -773,8 +817,13 @@ int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
   if (grid > num_sms()) grid = num_sms();
   ProfScope ps_(PK_PROP, st);
   {
-    static bool cfg = false;
-    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    static bool cfg = false;      // (the trace build carries 8 B of static shared memory)
+#ifdef PSVO_TC_TRACE
+    const int max_dyn = 227 * 1024 - 1024;
+#else
+    const int max_dyn = 227 * 1024;
+#endif
+    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)); cfg = true; }
     smc_propagate_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(a);
   }
   PSVO_LAUNCH_CHECK();

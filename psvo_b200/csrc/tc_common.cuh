@@ -124,6 +124,13 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
 }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------------
+// one lane of a fully converged warp; unlike `lane == 0` ptxas knows the guarded region runs on a single thread and
+// emits the tcgen05 instructions without a per-active-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(mbar)) : "memory");
 }
@@ -209,6 +216,37 @@ __device__ __forceinline__ void split8_f16_trunc(const float (&x)[8], uint4& hi,
     const __half2 ll = __floats2half2_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ReLU + truncating fp16 split of 8 raw pre-activations in six instructions per pair instead of eight, spread over the
+// FMA and ALU pipes.  cvt.*.relu.f16x2 applies the ReLU inside the packing conversion, so no FMNMX is needed:
+//   even pairs:  hi_f = x & 0xFFFFE000 (LOP3, ALU) ; lo_f = x - hi_f ; hi = pack.relu(hi_f) ; lo = pack.relu(lo_f)
+//   odd pairs :  hi = pack.rz.relu(x) ; hi_f = float(hi) (HADD2.F32, FMA pipe) ; lo_f = x - hi_f ; lo = pack.relu(lo_f)
+// For x < 0 both give hi = lo = 0 (hi_f and lo_f are <= 0); for x >= 0 both give hi = trunc11(x), lo = rn(x - hi).
+__device__ __forceinline__ uint32_t pack_relu_rn(float x0, float x1) {
+  uint32_t r; asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0)); return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_rz(float x0, float x1) {
+  uint32_t r; asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0)); return r;
+}
+__device__ __forceinline__ void split8_relu_f16(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x0 = x[2 * i], x1 = x[2 * i + 1];
+    if (i & 1) {
+      h[i] = pack_relu_rz(x0, x1);
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+      l[i] = pack_relu_rn(x0 - hf.x, x1 - hf.y);
+    } else {
+      const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+      const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+      h[i] = pack_relu_rn(h0, h1);
+      l[i] = pack_relu_rn(x0 - h0, x1 - h1);
+    }
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

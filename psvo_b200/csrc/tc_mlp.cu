@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
     tc::fence_before_sync();
     __syncthreads();
     // ---- layer 1
-    if (tid == 0) {
+    if (tid < 32 && tc::elect_one()) {
       tc::fence_after_sync();
       const uint64_t dah = tc::make_desc(a1h, 2048, 128), dal = tc::make_desc(a1l, 2048, 128);
       const uint64_t dbh = tc::make_desc(w1h, H * 16, 128), dbl = tc::make_desc(w1l, H * 16, 128);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) particle_mlp_tc_kernel(psvo_mlp net, cons
     tc::fence_before_sync();
     __syncthreads();
     // ---- layer 2
-    if (tid == 0) {
+    if (tid < 32 && tc::elect_one()) {
       tc::fence_after_sync();
       for (int s = 0; s < H / 16; ++s) {
         const uint64_t dah = tc::make_desc(a2h + s * 4096, 2048, 128), dal = tc::make_desc(a2l + s * 4096, 2048, 128);
