@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     const float spv = two_q ? 1.0f / (i1 + i2) : s1;
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
-  if (tid >= 32 && tid < 64) C[96 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
+  if (tid >= 32 && tid < 64) C[96 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
   if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
   if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
     const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
@@ -346,12 +346,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       // ---- per-sequence rows every particle of the tile shares (second proposal mean, observation): one global load
       //      per thread into the group's double-buffered slot instead of 48 dependent broadcast loads per thread
       const float* rc = reinterpret_cast<const float*>(sm + L.rowc) + (grp * 2 + (tile_it & 1)) * 64;
-      {
-        float* rcw = const_cast<float*>(rc);
-        if (two_q && gt < Dx) rcw[gt] = __ldg(a.mu2_all + bt * Dx + gt);
-        if (gt >= 32 && gt < 32 + Dy) rcw[16 + gt - 32] = __ldg(a.obs + bt * Dy + gt - 32);
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      }
+      float rowv = 0.0f;                                                   // loaded now, parked in the slot after the Philox work
+      if (two_q && gt < Dx) rowv = __ldg(a.mu2_all + bt * Dx + gt);
+      if (gt >= 32 && gt < 32 + Dy) rowv = __ldg(a.obs + bt * Dy + gt - 32);
       ++tile_it;
       float x[16], mu1[16];
       // ---- d1 mean: MLP q1 on the resampled parent (t >= 1) or the per-sequence q0 mean (t = 0)
@@ -382,6 +379,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
           else { e[4 * c] = e[4 * c + 1] = e[4 * c + 2] = e[4 * c + 3] = 0.f; }
         }
       }
+      {
+        float* rcw = const_cast<float*>(rc);
+        if (gt < 16) rcw[gt] = rowv;
+        if (gt >= 32 && gt < 64) rcw[16 + gt - 32] = rowv;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
       if (!t0) {
         tc_mlp_compute(g, x, nchunk);
         float mb[16];
@@ -396,13 +399,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
 
       // ---- proposal (fusion), sample, q / f log densities   (f = d1: use_bootstrap, SVO.py:230)
       float qs = 0.f, fsum = 0.f;
+      float mq[16];                                                        // proposal mean (fusion of d1 and d2, SVO.py:182-197)
+      if (two_q) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 m2 = reinterpret_cast<const float4*>(rc)[v];       // rows beyond Dx hold 0
+          mq[4 * v] = sp[4 * v] * (inv1[4 * v] * mu1[4 * v] + inv2[4 * v] * m2.x);
+          mq[4 * v + 1] = sp[4 * v + 1] * (inv1[4 * v + 1] * mu1[4 * v + 1] + inv2[4 * v + 1] * m2.y);
+          mq[4 * v + 2] = sp[4 * v + 2] * (inv1[4 * v + 2] * mu1[4 * v + 2] + inv2[4 * v + 2] * m2.z);
+          mq[4 * v + 3] = sp[4 * v + 3] * (inv1[4 * v + 3] * mu1[4 * v + 3] + inv2[4 * v + 3] * m2.w);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) mq[d] = mu1[d];
+      }
 #pragma unroll
       for (int d = 0; d < 16; ++d) {
-        float m = mu1[d];
-        if (two_q) {
-          const float m2 = d < Dx ? rc[d] : 0.0f;
-          m = sp[d] * (inv1[d] * mu1[d] + inv2[d] * m2);
-        }
+        const float m = mq[d];
         const float X = fmaf(sp[d], e[d], m);
         const float zq = (X - m) * inv_sp[d];
         const float zf = (X - mu1[d]) * inv_s1[d];
@@ -432,14 +445,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         float mug[16], mgb[16];
         tc::tmem_ld16(g.tD2 + c, mug);
         tc::tmem_ld16(g.tD2 + NPG + c, mgb);
+        if (!poisson) {                                                    // branch-free Gaussian emission; columns beyond Dy: y = b2 = 0
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int d = c + i;
-          if (d < Dy) {
-            const float y = rc[16 + d];
+          for (int i = 0; i < 16; ++i) {
+            const int d = c + i;
             const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
-            const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
+            const float z = (rc[16 + d] - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int d = c + i;
+            if (d < Dy) {
+              const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
+              const float z = rc[16 + d] - (softplus(mu) + 1e-6f);
+              gsum = fmaf(z, z, gsum);
+            }
           }
         }
       }
