@@ -50,6 +50,7 @@ extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_trace(long l
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
+constexpr int kTcBars = 8;             // mbarriers per group (5 used)
 // exact power-of-two operand scales: W1 (and its bias) by 2^4, W2 by 2^8 -> their fp16 lo halves stay normal; the hidden
 // activations travel in 16x units (|h| < 4094) and the layer-2 accumulator in 4096x units, undone in the output FFMA
 constexpr float kW1Scale = 16.0f, kW2Scale = 256.0f, kWUnscale = 1.0f / (16.0f * 256.0f);
@@ -59,7 +60,7 @@ struct TcPropSmem {
   uint32_t w1q_b, w1g_b;                               // layer-1 bias as a B operand [H x K=16]: k=0 b_hi, k=1 b_lo
   uint32_t a_ones;                                     // its A operand [128 x K=16]: k=0,1 = 1 (same for every row)
   uint32_t b1q, b2q, b1g, b2g, consts;                                        // fp32
-  uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups], a2_hi[kTcGroups], a2_lo[kTcGroups];
+  uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups];        // layer-1 A operands; the layer-2 A operand lives in tensor memory
   uint32_t rowc;                                       // per group, two tile parities: [mu2 (16) | obs (32) | pad] fp32
   uint32_t bars, slot, total;
 };
@@ -77,11 +78,10 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   s.consts = PSVO_TAKE(160 * 4);
   for (int g = 0; g < kTcGroups; ++g) {
     s.a1_hi[g] = PSVO_TAKE(128 * 16 * 2); s.a1_lo[g] = PSVO_TAKE(128 * 16 * 2);
-    s.a2_hi[g] = PSVO_TAKE(128 * kTcChunk * 2); s.a2_lo[g] = PSVO_TAKE(128 * kTcChunk * 2);
   }
   s.a_ones = PSVO_TAKE(128 * 16 * 2);
   s.rowc = PSVO_TAKE(kTcGroups * 2 * 64 * 4);
-  s.bars = PSVO_TAKE(4 * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full, mD1[0], mD1[1], mL2
+  s.bars = PSVO_TAKE(kTcBars * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full[0], mD1[0], mD1[1], mL2, mDone, full[1]
 #undef PSVO_TAKE
   s.total = o;
   return s;
@@ -90,10 +90,10 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
 struct TcNetDesc { uint64_t w1h, w1l, w1b, w2; uint32_t idesc2a, idesc2b; int NP; };
 
 struct TcGroup {
-  unsigned char *pa2h, *pa2l;      // this thread's 16-byte slot in the A2 operand (K-group 0)
-  unsigned char *pa1h, *pa1l;      // same for A1
-  uint64_t *full, *mD1, *mL2;      // full: operand staged (128 arrivals) ; mD1[0..1]: L1 into D1 buffer done ; mL2: L2 done
-  uint32_t par;                    // parities of the next completions: bit 0/1 = mD1[0/1], bit 2 = mL2
+  unsigned char *pa1h, *pa1l;      // this thread's 16-byte slot in the A1 operand (K-group 0)
+  uint64_t *full, *mD1, *mDone;    // full[0], full[5]: operand staged (128 arrivals, alternating) ; mD1[0..1]: L1 into D1 buffer done ; mDone: last L2 done
+  uint32_t par;                    // parities of the next completions: bit 0/1 = mD1[0/1], bit 2 = mDone
+  uint32_t k;                      // arrivals so far: arrival k goes to full[(k & 1) * 5]
   uint32_t tD1, tD2;               // TMEM addresses incl. this warp's lane offset: D1[1] = tD1 + 32 ; D2 = 2*NP columns
 };
 
@@ -105,9 +105,20 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
   par ^= 1u << BIT;
 }
 
-// hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> scale + bias -> ReLU -> fp16 hi/lo -> A2 -> arrive
+// "operand staged" arrivals alternate between two mbarriers.  The compute threads may run one stage ahead of the MMA warp
+// (arrival k only proves that stage k-2 was consumed: L1(c) is issued at stage c-1), and two completions of ONE mbarrier
+// before the consumer's parity test would be indistinguishable from none.
+__device__ __forceinline__ void tc_arrive(TcGroup& g) {
+  tc::mbar_arrive(g.full + (g.k & 1u) * 5u);
+  ++g.k;
+}
+
+// hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> ReLU -> fp16 hi/lo -> back into the SAME 32 TMEM columns as
+// the layer-2 A operand (columns 0-15: hi, two hidden units per column; 16-31: lo) -> arrive.  The activations never touch
+// shared memory: no st.shared, no generic->async proxy fence, and the two D1 buffers double-buffer the operand for free.
 template <int BUF>
 __device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
+  (void)c;
   TC_TRACE(1);
   tc_wait<BUF>(g.mD1 + BUF, g.par);                                       // L1(c) complete
   tc::fence_after_sync();
@@ -115,25 +126,23 @@ __device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
   float v[32];
   tc::tmem_ld32(g.tD1 + BUF * 32, v);
   TC_TRACE(3);
-  uint4 hi[4], lo[4];
+  uint32_t r[32];
 #pragma unroll
   for (int kg = 0; kg < 4; ++kg) {
     float h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = v[kg * 8 + i];                      // D1 = 16 (W1^T x + b1): the bias rode in the MMA
-    tc::split8_relu_f16(h, hi[kg], lo[kg]);                                // ReLU inside the packing conversion
+    uint4 hi, lo;
+    tc::split8_relu_f16(h, hi, lo);                                        // ReLU inside the packing conversion
+    r[4 * kg] = hi.x; r[4 * kg + 1] = hi.y; r[4 * kg + 2] = hi.z; r[4 * kg + 3] = hi.w;
+    r[16 + 4 * kg] = lo.x; r[16 + 4 * kg + 1] = lo.y; r[16 + 4 * kg + 2] = lo.z; r[16 + 4 * kg + 3] = lo.w;
   }
   TC_TRACE(4);
-  if (c > 0) tc_wait<2>(g.mL2, g.par);                                     // L2(c-1) complete -> A2 reusable
+  tc::tmem_st32(g.tD1 + BUF * 32, r);
+  tc::tmem_st_wait();
   TC_TRACE(5);
-#pragma unroll
-  for (int kg = 0; kg < 4; ++kg) {
-    *reinterpret_cast<uint4*>(g.pa2h + kg * 2048) = hi[kg];
-    *reinterpret_cast<uint4*>(g.pa2l + kg * 2048) = lo[kg];
-  }
-  tc::fence_proxy_async();
   tc::fence_before_sync();
-  tc::mbar_arrive(g.full);                                                 // A2(c) staged, D1[BUF] released
+  tc_arrive(g);                                                            // A2(c) staged in D1[BUF]
   TC_TRACE(6);
 }
 
@@ -152,12 +161,12 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16],
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
-  tc::mbar_arrive(g.full);
+  tc_arrive(g);
   for (int c = 0; c < nchunk; c += 2) {
     tc_chunk<0>(g, c);
     if (c + 1 < nchunk) tc_chunk<1>(g, c + 1);
   }
-  tc_wait<2>(g.mL2, g.par);                                                // L2(last) complete
+  tc_wait<2>(g.mDone, g.par);                                              // L2(last) complete
   tc::fence_after_sync();
 }
 
@@ -173,34 +182,34 @@ __device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, u
   tc::mma_bf16(d, aones, nd.w1b + off, idesc1, true);                      // + 16 b1 (hi + lo)
   tc::mma_commit(mD1 + (c & 1));
 }
-// L2(c): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)  and  a_lo x w_hi (N = NP)
-__device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint64_t a2h, uint64_t a2l, uint32_t tD2, int c, uint64_t* mL2) {
+// L2(c), A operand in TMEM (D1[c & 1]): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)  and  a_lo x w_hi (N = NP)
+__device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint32_t tD1, uint32_t tD2, int c) {
+  const uint32_t a = tD1 + (c & 1) * 32;
 #pragma unroll
   for (int ks = 0; ks < kTcChunk / 16; ++ks) {
     const uint64_t b = nd.w2 + (uint64_t)((uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(2 * nd.NP));   // (2*NP*16 B per K-group) >> 4
-    const uint64_t ah = a2h + (uint64_t)(ks * (4096 / 16)), al = a2l + (uint64_t)(ks * (4096 / 16));
-    tc::mma_bf16(tD2, ah, b, nd.idesc2a, (c > 0) || (ks > 0));
-    tc::mma_bf16(tD2, al, b, nd.idesc2b, true);
+    tc::mma_f16_ts(tD2, a + 8 * ks, b, nd.idesc2a, (c > 0) || (ks > 0));
+    tc::mma_f16_ts(tD2, a + 16 + 8 * ks, b, nd.idesc2b, true);
   }
-  tc::mma_commit(mL2);
 }
 
 // MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1) the
-// chunk schedule  L1(0), L1(1) | L2(c-1), L1(c+1) ...  driven by the group's "operand staged" barrier.
+// chunk schedule  L1(0), L1(1) | L2(c), L1(c+2) ...  driven by the group's "operand staged" barrier.  L1(c+2) overwrites
+// the columns L2(c) reads its A operand from, so it is issued only after L2(c) has completed (mL2).
 __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem& L, uint32_t tmem, uint64_t* bars, int grp, int lane,
                                             int work, int nchunk, int first_net, const TcNetDesc& nq, const TcNetDesc& ng) {
-  uint64_t* full = bars + 4 * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3;
+  (void)lane;
+  uint64_t* full = bars + kTcBars * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3; uint64_t* mDone = full + 4;
   const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
-  const uint64_t a2h = tc::make_desc(tc::smem_u32(sm + L.a2_hi[grp]), 2048, 128), a2l = tc::make_desc(tc::smem_u32(sm + L.a2_lo[grp]), 2048, 128);
   const uint64_t aones = tc::make_desc(tc::smem_u32(sm + L.a_ones), 2048, 128);
   const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
-  uint32_t phase = 0;
+  uint32_t k = 0, ph2 = 0;
   for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
     for (int net = first_net; net < 2; ++net) {
       const TcNetDesc& nd = net ? ng : nq;
       for (int s2 = 0; s2 <= nchunk; ++s2) {
         TC_TRACE(10);
-        tc::mbar_wait(full, phase); phase ^= 1;
+        tc::mbar_wait(full + (k & 1u) * 5u, (k >> 1) & 1u); ++k;
         tc::fence_after_sync();
         TC_TRACE(11);
         if (tc::elect_one()) {
@@ -208,9 +217,17 @@ __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem&
             tc_issue_l1(nd, a1h, a1l, aones, tD1, 0, mD1);
             if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, aones, tD1, 1, mD1);
           } else {
-            tc_issue_l2(nd, a2h, a2l, tD2, s2 - 1, mL2);
-            TC_TRACE(13);
-            if (s2 + 1 < nchunk) tc_issue_l1(nd, a1h, a1l, aones, tD1, s2 + 1, mD1);
+            const int c = s2 - 1;
+            tc_issue_l2(nd, tD1, tD2, c);
+            if (c + 2 < nchunk) {
+              tc::mma_commit(mL2);
+              TC_TRACE(13);
+              tc::mbar_wait(mL2, ph2); ph2 ^= 1;                            // A2(c) consumed -> D1[c & 1] reusable
+              tc::fence_after_sync();
+              tc_issue_l1(nd, a1h, a1l, aones, tD1, c + 2, mD1);
+            } else if (c + 1 == nchunk) {
+              tc::mma_commit(mDone);
+            }
           }
         }
         TC_TRACE(12);
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][4]: full, mD1[0], mD1[1], mL2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][kTcBars]: full, mD1[0], mD1[1], mL2, mDone
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
 
   // ---- weights (fp16 hi/lo, UMMA B layout, pre-scaled) and biases: one coalesced copy of the image that
@@ -283,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
-  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
   if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
     const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
     *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -328,9 +345,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     (void)s1;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
     g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
 
@@ -515,7 +531,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     C[48 + d] = 1.0f / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
   }
   if (tid >= 32 && tid < 64) C[64 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
-  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
   if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
     const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
     *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -557,9 +573,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
     g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
 
@@ -677,7 +692,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
 #pragma unroll 4
     for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  if (tid < 4 * kTcGroups) tc::mbar_init(bars + tid, (tid & 3) == 0 ? 128 : 1);
+  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
   if (tid < 256) {
     const uint32_t one2 = 0x3C003C00u;
     *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -707,9 +722,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
     const int grp = warp >> 2;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + 4 * grp; g.mD1 = g.full + 1; g.mL2 = g.full + 3; g.par = 0;
+    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
     g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    g.pa2h = sm + L.a2_hi[grp] + gt * 16; g.pa2l = sm + L.a2_lo[grp] + gt * 16;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
