@@ -217,8 +217,13 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
     size_t psm = 0; int pblk = 0;
     if (persistent_filter_supported(pa, plan, &psm, &pblk)) return launch_filter_persistent(pa, ra, plan, st);
   }
+  // tensor-core path: the ancestor gather X_anc[t] = Xs[t][anc[t]] is folded into the propagate launch of t+1 (which
+  // needs the parents anyway), so only the last step's resample launch moves particle states
+  const bool fuse_gather = pa.tc_image != nullptr;
   for (int t = 0; t < d->T; ++t) {
     pa.t = t; ra.t = t;
+    pa.anc_prev = fuse_gather && t > 0 ? anc : nullptr; pa.X_anc_w = X_anc;
+    ra.skip_gather = fuse_gather && t + 1 < d->T ? 1 : 0;
     if (int e = launch_propagate(pa, plan, st)) return e;
     if (int e = launch_resample(ra, st)) return e;
   }

@@ -13,6 +13,7 @@
 // HBM layout is sequence-major (B,T,N,D): every (b,t) slab a kernel touches is contiguous.
 #include <stdlib.h>
 #include "mlp_tile.cuh"
+#include <cstdlib>
 #include "smc_kernels.h"
 
 namespace psvo {
@@ -437,6 +438,7 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
   }
   __syncthreads();
 
+  if (a.skip_gather) return;                     // the propagate launch of t+1 gathers (PropArgs::anc_prev)
   // ancestor gather X_anc[t][n] = X_t[anc[n]]: consecutive threads write consecutive 16-byte pieces of the children
   const float* Xt = a.Xs + bt * N * Dx;
   float* Xa = a.X_anc + bt * N * Dx;
@@ -599,8 +601,14 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   int parts = 1;
   while (parts < 4 && (long long)a.B * parts < 2LL * num_sms() && N / (parts * 2) >= 512) parts *= 2;
   while (parts < 64 && (size_t)N * 12 + (size_t)((N + parts - 1) / parts) * 4 > 220 * 1024) parts *= 2;   // ancestor scratch must fit
+  // without the gather (fused into the next propagate launch) one CTA per sequence is best: the CDF is built once and
+  // 1024 threads keep four interleaved searches each in flight (measured at config 5: 25 us vs 32 us with 4 parts)
+  if (a.skip_gather && (size_t)N * 16 <= 220 * 1024) {
+    parts = 1;
+    while (parts < 4 && (long long)a.B * parts * 2 < num_sms() && N / (parts * 2) >= 512) parts *= 2;
+  }
   const int chunk = (N + parts - 1) / parts;
-  int block = N >= 4096 ? 512 : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));
+  int block = N >= 4096 ? (a.skip_gather ? 1024 : 512) : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));
   const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float)) + (size_t)chunk * sizeof(int);
   PSVO_REQUIRE(smem <= 220 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 220 KiB)", N, smem);
   static size_t configured = 0;

@@ -28,6 +28,10 @@ struct PropArgs {
   float* Xs;               // (B,T,N,Dx) written at t
   float* log_Ws;           // (B,T,N)    written at t
   const unsigned char* tc_image;   // staged fp16 weight image for the tensor-core path (launch_tc_stage_image) or NULL
+  // fused ancestor gather (tensor-core path): when anc_prev != NULL the parent of particle n is read as Xs[t-1][anc_prev[t-1][n]]
+  // and copied to X_anc_w[t-1][n]; the resample launch of t-1 then skipped its own gather (ResampleArgs::skip_gather)
+  const int* anc_prev = nullptr;   // (B,T,N)
+  float* X_anc_w = nullptr;        // (B,T,N,Dx)
   unsigned long long seed;
   int N, B, T, Dx, Dy, t, seq_offset, scratch_half;
   unsigned flags;
@@ -50,6 +54,7 @@ struct ResampleArgs {
   int N, B, T, Dx, t, seq_offset;
   unsigned flags;
   unsigned stream_id;      // Philox stream of the uniforms (1 forward filter, 4 PSVOwR second resampling)
+  int skip_gather = 0;     // 1: write anc only; X_anc[t] is produced by the propagate launch of t+1 (PropArgs::anc_prev)
 };
 int launch_resample(const ResampleArgs& a, cudaStream_t st);
 

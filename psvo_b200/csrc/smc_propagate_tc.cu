@@ -367,21 +367,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       if (gt >= 32 && gt < 32 + Dy) rowv = __ldg(a.obs + bt * Dy + gt - 32);
       ++tile_it;
       float x[16], mu1[16];
-      // ---- d1 mean: MLP q1 on the resampled parent (t >= 1) or the per-sequence q0 mean (t = 0)
+      // ---- d1 mean: MLP q1 on the resampled parent (t >= 1) or the per-sequence q0 mean (t = 0).  With the fused
+      //      gather the parent row is Xs[t-1][anc[t-1][n]] (L2-resident: the previous launch wrote it) and is also
+      //      copied to X_anc[t-1][n], the reference's log["Xs"] output (SVO.py:54)
+      const float* xsrc = nullptr;
       if (!t0) {
-        const float* src = a.X_anc + ((bt - 1) * N + (live ? n : 0)) * Dx;
-        if (Dx == 16) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const float4 q = reinterpret_cast<const float4*>(src)[v];
-            x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
-          }
-        } else {
-#pragma unroll
-          for (int d = 0; d < 16; ++d) x[d] = d < Dx ? src[d] : 0.0f;
-        }
+        const size_t prow = (bt - 1) * N + (live ? n : 0);
+        xsrc = a.anc_prev != nullptr ? a.Xs + ((bt - 1) * N + __ldg(a.anc_prev + prow)) * Dx : a.X_anc + prow * Dx;
       }
-      // noise for this particle
+      // noise for this particle (the Philox work also covers the latency of the ancestor index load above)
       float e[16];
       if (a.eps != nullptr) {
         const float* src = a.eps + row * Dx;
@@ -390,9 +384,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       } else {
         const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n : 0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
           else { e[4 * c] = e[4 * c + 1] = e[4 * c + 2] = e[4 * c + 3] = 0.f; }
+        }
+      }
+      if (!t0) {
+        if (Dx == 16) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 q = reinterpret_cast<const float4*>(xsrc)[v];
+            x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < 16; ++d) x[d] = d < Dx ? xsrc[d] : 0.0f;
+        }
+      }
+      if (a.eps == nullptr) {
+        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n : 0);
+#pragma unroll
+        for (int c = 2; c < 4; ++c) {
+          if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
+          else { e[4 * c] = e[4 * c + 1] = e[4 * c + 2] = e[4 * c + 3] = 0.f; }
+        }
+      }
+      if (!t0 && a.anc_prev != nullptr && live) {
+        float* dst = a.X_anc_w + ((bt - 1) * N + n) * Dx;
+        if (Dx == 16) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) reinterpret_cast<float4*>(dst)[v] = make_float4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int d = 0; d < 16; ++d) if (d < Dx) dst[d] = x[d];
         }
       }
       {
