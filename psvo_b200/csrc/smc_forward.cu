@@ -324,9 +324,13 @@ int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------
 // normalise + resample + gather for sequence b at time t, children of part `part` of `nparts`; NC: X_t may be read
 // through the non-coherent path (only when a previous kernel wrote it)
+// sG (optional, K+1 ints with K = 2^kbits >= N): guide table G[k] = #{j : C[j] <= B_k} over the K equal slices of the
+// uniform's 24-bit range (B_k = draw_threshold(total, k 2^24/K)).  A child whose uniform falls in slice k has its ancestor in
+// [G[k], G[k+1]] -- about one particle wide -- so the inverse-CDF search is 1-2 probes of the CDF instead of log2 N
+// bank-conflicting ones; the result is the same upper bound, bit for bit.
 template <bool NC>
 __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int part, int nparts, int t, unsigned char* smraw,
-                                              unsigned long long* sscr, float* fscr) {
+                                              unsigned long long* sscr, float* fscr, int* sG = nullptr, int kbits = 0) {
   const int N = a.N, Dx = a.Dx;
   unsigned long long* sC = reinterpret_cast<unsigned long long*>(smraw);
   float* sLW = reinterpret_cast<float*>(sC + N);
@@ -389,11 +393,62 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
   const bool resample = a.flags & PSVO_F_RESAMPLE;
   int top = 1;                                   // largest power of two <= N
   while (top * 2 <= N) top *= 2;
+  const bool guided = sG != nullptr && resample && a.forced_anc == nullptr;
+  const int K = 1 << kbits, gs = 24 - kbits;
+  if (guided) {
+    for (int i = tid; i <= K; i += nt) sG[i] = 0;
+    __syncthreads();
+    // kf(j) = min{k : B_k >= C[j]}: float estimate, exact integer fix-up; histogram, then G = inclusive scan
+    const float scale = (float)K / (float)total;
+    for (int j = tid; j < N; j += nt) {
+      const unsigned long long c = sC[j];
+      int kf = (int)((float)c * scale);
+      kf = kf < 0 ? 0 : (kf > K ? K : kf);
+      while (kf > 0 && draw_threshold(total, (uint32_t)(kf - 1) << gs) >= c) --kf;
+      while (kf < K && draw_threshold(total, (uint32_t)kf << gs) < c) ++kf;
+      atomicAdd(&sG[kf], 1);
+    }
+    __syncthreads();
+    const int nG = K + 1;
+    const int pw = (((nG + nw - 1) / nw) + 31) & ~31;
+    const int g_lo = min(wid * pw, nG), g_hi = min(g_lo + pw, nG);
+    int gcarry = 0;
+    for (int base = g_lo; base < g_hi; base += 32) {
+      const int i = base + lane;
+      int v = i < g_hi ? sG[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += nb;
+      }
+      v += gcarry;
+      if (i < g_hi) sG[i] = v;
+      gcarry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    int* iscr = reinterpret_cast<int*>(fscr);      // 33 words, free after block_max
+    if (lane == 0) iscr[wid] = gcarry;
+    __syncthreads();
+    if (wid == 0) {
+      const int wt = lane < nw ? iscr[lane] : 0;
+      int inc = wt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+      }
+      if (lane < nw) iscr[lane] = inc - wt;
+    }
+    __syncthreads();
+    const int goff = iscr[wid];
+    if (goff != 0) for (int i = g_lo + lane; i < g_hi; i += 32) sG[i] += goff;
+    __syncthreads();
+  }
   // four children per thread at a time: their branch-free binary searches interleave, hiding the shared-memory latency
   for (int n0 = n_lo + tid; n0 < n_hi; n0 += 4 * nt) {
     unsigned long long thr[4];
     int anc[4];
     bool search[4];
+    int kb[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int n = n0 + k * nt;
@@ -414,16 +469,35 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
           if (systematic) u24 = (uint32_t)((((uint64_t)n << 24) + u24) / (uint64_t)N);   // floor(2^24 (n + u_0) / N)
           thr[k] = draw_threshold(total, u24);
           search[k] = true;
+          kb[k] = min((int)(u24 >> gs), K - 1);
         }
       }
     }
     // #{j : C[j] <= thr} (upper bound) by descending powers of two; identical to upper_bound_u64 on a monotone CDF
     int pos[4] = {0, 0, 0, 0};
-    for (int s = top; s > 0; s >>= 1) {
+    if (guided) {
+      int hi[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cand = pos[k] + s;
-        if (search[k] && cand <= N && sC[cand - 1] <= thr[k]) pos[k] = cand;
+      for (int k = 0; k < 4; ++k) { pos[k] = search[k] ? sG[kb[k]] : 0; hi[k] = search[k] ? sG[kb[k] + 1] : 0; }
+      bool any = true;
+      while (any) {                              // the four bracketed searches advance together
+        any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (pos[k] < hi[k]) {
+            const int mid = (pos[k] + hi[k]) >> 1;
+            if (sC[mid] <= thr[k]) pos[k] = mid + 1; else hi[k] = mid;
+            any = true;
+          }
+        }
+      }
+    } else {
+      for (int s = top; s > 0; s >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cand = pos[k] + s;
+          if (search[k] && cand <= N && sC[cand - 1] <= thr[k]) pos[k] = cand;
+        }
       }
     }
 #pragma unroll
@@ -476,11 +550,12 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
   }
 }
 
-__global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a) {
+__global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a, int guide_off, int kbits) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ unsigned long long sscr[33];
   __shared__ float fscr[33];
-  resample_body<true>(a, blockIdx.x, blockIdx.y, gridDim.y, a.t, smraw, sscr, fscr);
+  int* sG = guide_off > 0 ? reinterpret_cast<int*>(smraw + guide_off) : nullptr;
+  resample_body<true>(a, blockIdx.x, blockIdx.y, gridDim.y, a.t, smraw, sscr, fscr, sG, kbits);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -609,15 +684,22 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   }
   const int chunk = (N + parts - 1) / parts;
   int block = N >= 4096 ? (a.skip_gather ? 1024 : 512) : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));
-  const size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float)) + (size_t)chunk * sizeof(int);
+  size_t smem = (size_t)N * (sizeof(unsigned long long) + sizeof(float)) + (size_t)chunk * sizeof(int);
   PSVO_REQUIRE(smem <= 220 * 1024, "n_particles=%d needs %zu B of shared memory for the CDF (max 220 KiB)", N, smem);
+  // guide table of the inverse-CDF search (K + 1 ints, K = 2^kbits >= N) when it fits and the search is long enough to pay
+  int kbits = 0, guide_off = 0;
+  while ((1 << kbits) < N) ++kbits;
+  if (N >= 256 && kbits <= 24 && smem + ((size_t)(1 << kbits) + 1) * sizeof(int) + 16 <= 220 * 1024) {
+    guide_off = (int)((smem + 15) & ~(size_t)15);
+    smem = (size_t)guide_off + ((size_t)(1 << kbits) + 1) * sizeof(int);
+  }
   static size_t configured = 0;
   if (smem > 40 * 1024 && smem > configured) {
     PSVO_CUDA(cudaFuncSetAttribute(smc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   ProfScope ps_(PK_RESAMPLE, st);
-  smc_resample_kernel<<<dim3(a.B, parts), block, smem, st>>>(a);
+  smc_resample_kernel<<<dim3(a.B, parts), block, smem, st>>>(a, guide_off, kbits);
   PSVO_LAUNCH_CHECK();
   return 0;
 }
