@@ -20,8 +20,9 @@ __global__ void __launch_bounds__(512, 1) bench(int N, int n_issuers, int iters,
   const uint64_t b = tc::make_desc(tc::smem_u32(sm), N * 16, 128);
   __syncthreads();
   const long long t0 = clock64();
-  if (warp < n_issuers && lane == 0) {
-    for (int i = 0; i < iters; ++i) tc::mma_bf16(tmem + warp * 32, a, b, idesc, i > 0);
+  (void)lane;
+  if (warp < n_issuers && tc::elect_one()) {      // elect.sync: no per-lane serialisation loop around the MMAs
+    for (int i = 0; i < iters; ++i) tc::mma_bf16(tmem + (warp % 2) * 256, a, b, idesc, i > 0);
     tc::mma_commit(bars + warp);
     tc::mbar_wait(bars + warp, 0);
   }
@@ -37,7 +38,7 @@ int main() {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 1024;
   printf("%4s %8s %22s %22s\n", "N", "issuers", "cycles/MMA per issuer", "pipe cycles per MMA");
-  for (int N : {16, 32}) for (int iss : {1, 2, 4, 8, 12, 16}) {
+  for (int N : {16, 32, 64, 128, 256}) for (int iss : {1, 2, 4, 8}) {
     bench<<<148, 512, 64 * 1024>>>(N, iss, iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
