@@ -91,10 +91,10 @@ struct TcNetDesc { uint64_t w1h, w1l, w1b, w2; uint32_t idesc2a, idesc2b; int NP
 
 struct TcGroup {
   unsigned char *pa1h, *pa1l;      // this thread's 16-byte slot in the A1 operand (K-group 0)
-  uint64_t *full, *mD1, *mDone;    // full[0], full[5]: operand staged (128 arrivals, alternating) ; mD1[0..1]: L1 into D1 buffer done ; mDone: last L2 done
-  uint32_t par;                    // parities of the next completions: bit 0/1 = mD1[0/1], bit 2 = mDone
+  uint64_t *full, *mD1, *mDone;    // full[0], full[5]: operand staged (128 arrivals, alternating) ; mD1: L1 into D1 done ; mDone: last L2 done
+  uint32_t par;                    // parities of the next completions: bit 0 = mD1, bit 2 = mDone
   uint32_t k;                      // arrivals so far: arrival k goes to full[(k & 1) * 5]
-  uint32_t tD1, tD2;               // TMEM addresses incl. this warp's lane offset: D1[1] = tD1 + 32 ; D2 = 2*NP columns
+  uint32_t tD1, tD2;               // TMEM addresses incl. this warp's lane offset: D1 = 64 columns (one chunk) ; D2 = 2*NP columns
 };
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
@@ -113,36 +113,37 @@ __device__ __forceinline__ void tc_arrive(TcGroup& g) {
   ++g.k;
 }
 
-// hidden-layer chunk c (D1 buffer BUF = c & 1): TMEM row -> ReLU -> fp16 hi/lo -> back into the SAME 32 TMEM columns as
-// the layer-2 A operand (columns 0-15: hi, two hidden units per column; 16-31: lo) -> arrive.  The activations never touch
-// shared memory: no st.shared, no generic->async proxy fence, and the two D1 buffers double-buffer the operand for free.
-template <int BUF>
-__device__ __forceinline__ void tc_chunk(TcGroup& g, int c) {
-  (void)c;
+// hidden-layer chunk (up to 64 hidden units = `halves` blocks of 32 TMEM columns, ONE layer-1 accumulator): per block
+// TMEM row -> ReLU -> fp16 hi/lo -> back into the SAME 32 columns as the layer-2 A operand (columns 0-15: hi, two hidden
+// units per column; 16-31: lo) -> arrive, so layer 2 of the first block runs while the second is being converted.
+// The activations never touch shared memory: no st.shared, no generic->async proxy fence.
+__device__ __forceinline__ void tc_chunk(TcGroup& g, int halves) {
   TC_TRACE(1);
-  tc_wait<BUF>(g.mD1 + BUF, g.par);                                       // L1(c) complete
+  tc_wait<0>(g.mD1, g.par);                                               // L1 of the chunk complete
   tc::fence_after_sync();
   TC_TRACE(2);
-  float v[32];
-  tc::tmem_ld32(g.tD1 + BUF * 32, v);
-  TC_TRACE(3);
-  uint32_t r[32];
 #pragma unroll
-  for (int kg = 0; kg < 4; ++kg) {
-    float h[8];
+  for (int hb = 0; hb < 2; ++hb) {
+    if (hb < halves) {
+      float v[32];
+      tc::tmem_ld32(g.tD1 + hb * 32, v);
+      uint32_t r[32];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = v[kg * 8 + i];                      // D1 = 16 (W1^T x + b1): the bias rode in the MMA
-    uint4 hi, lo;
-    tc::split8_relu_f16(h, hi, lo);                                        // ReLU inside the packing conversion
-    r[4 * kg] = hi.x; r[4 * kg + 1] = hi.y; r[4 * kg + 2] = hi.z; r[4 * kg + 3] = hi.w;
-    r[16 + 4 * kg] = lo.x; r[16 + 4 * kg + 1] = lo.y; r[16 + 4 * kg + 2] = lo.z; r[16 + 4 * kg + 3] = lo.w;
+      for (int kg = 0; kg < 4; ++kg) {
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = v[kg * 8 + i];                  // D1 = 16 (W1^T x + b1): the bias rode in the MMA
+        uint4 hi, lo;
+        tc::split8_relu_f16(h, hi, lo);                                    // ReLU inside the packing conversion
+        r[4 * kg] = hi.x; r[4 * kg + 1] = hi.y; r[4 * kg + 2] = hi.z; r[4 * kg + 3] = hi.w;
+        r[16 + 4 * kg] = lo.x; r[16 + 4 * kg + 1] = lo.y; r[16 + 4 * kg + 2] = lo.z; r[16 + 4 * kg + 3] = lo.w;
+      }
+      tc::tmem_st32(g.tD1 + hb * 32, r);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc_arrive(g);                                                        // A2 block staged in D1
+    }
   }
-  TC_TRACE(4);
-  tc::tmem_st32(g.tD1 + BUF * 32, r);
-  tc::tmem_st_wait();
-  TC_TRACE(5);
-  tc::fence_before_sync();
-  tc_arrive(g);                                                            // A2(c) staged in D1[BUF]
   TC_TRACE(6);
 }
 
@@ -162,27 +163,25 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16],
   tc::fence_proxy_async();
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
   tc_arrive(g);
-  for (int c = 0; c < nchunk; c += 2) {
-    tc_chunk<0>(g, c);
-    if (c + 1 < nchunk) tc_chunk<1>(g, c + 1);
-  }
+  for (int c = 0; c < nchunk; c += 2) tc_chunk(g, nchunk - c < 2 ? nchunk - c : 2);   // nchunk counts blocks of 32 hidden units
   tc_wait<2>(g.mDone, g.par);                                              // L2(last) complete
   tc::fence_after_sync();
 }
 
-// MMA-warp side (one elected lane): L1(c) -> D1[c & 1]
-__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t aones, uint32_t tD1, int c,
+// MMA-warp side (one elected lane): L1 of the chunk starting at block c (c even; `halves` blocks of 32 hidden units) -> D1.
+// One N = 64 instruction costs 48 tensor-pipe cycles against 2 x 40 for two N = 32 ones (profiles/microbench).
+__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t aones, uint32_t tD1, int c, int halves,
                                             uint64_t* mD1) {
-  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
-  const uint32_t d = tD1 + (c & 1) * 32;
+  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk * halves);
   const uint64_t off = (uint64_t)(c * (kTcChunk * 16 / 16));
-  tc::mma_bf16(d, a1h, nd.w1h + off, idesc1, false);
-  tc::mma_bf16(d, a1h, nd.w1l + off, idesc1, true);
-  tc::mma_bf16(d, a1l, nd.w1h + off, idesc1, true);
-  tc::mma_bf16(d, aones, nd.w1b + off, idesc1, true);                      // + 16 b1 (hi + lo)
-  tc::mma_commit(mD1 + (c & 1));
+  tc::mma_bf16(tD1, a1h, nd.w1h + off, idesc1, false);
+  tc::mma_bf16(tD1, a1h, nd.w1l + off, idesc1, true);
+  tc::mma_bf16(tD1, a1l, nd.w1h + off, idesc1, true);
+  tc::mma_bf16(tD1, aones, nd.w1b + off, idesc1, true);                    // + 16 b1 (hi + lo)
+  tc::mma_commit(mD1);
 }
-// L2(c), A operand in TMEM (D1[c & 1]): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)  and  a_lo x w_hi (N = NP)
+// L2 of block c (32 hidden units), A operand in TMEM (D1 columns [32 (c & 1), +32)): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)
+// and  a_lo x w_hi (N = NP)
 __device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint32_t tD1, uint32_t tD2, int c) {
   const uint32_t a = tD1 + (c & 1) * 32;
 #pragma unroll
@@ -194,8 +193,9 @@ __device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint32_t tD1, u
 }
 
 // MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1) the
-// chunk schedule  L1(0), L1(1) | L2(c), L1(c+2) ...  driven by the group's "operand staged" barrier.  L1(c+2) overwrites
-// the columns L2(c) reads its A operand from, so it is issued only after L2(c) has completed (mL2).
+// schedule  L1(chunk 0) | L2(block c) per staged block, and after the chunk's last block L1(next chunk)  driven by the
+// group's "operand staged" barriers.  L1 of the next chunk overwrites the columns the chunk's L2s read their A operand from,
+// so it is issued only after they have completed (mL2); the other three groups keep the tensor pipe busy meanwhile.
 __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem& L, uint32_t tmem, uint64_t* bars, int grp, int lane,
                                             int work, int nchunk, int first_net, const TcNetDesc& nq, const TcNetDesc& ng) {
   (void)lane;
@@ -207,25 +207,25 @@ __device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem&
   for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
     for (int net = first_net; net < 2; ++net) {
       const TcNetDesc& nd = net ? ng : nq;
-      for (int s2 = 0; s2 <= nchunk; ++s2) {
+      for (int c = -1; c < nchunk; ++c) {                                  // c = -1: the network's input operand A1 is staged
         TC_TRACE(10);
         tc::mbar_wait(full + (k & 1u) * 5u, (k >> 1) & 1u); ++k;
         tc::fence_after_sync();
         TC_TRACE(11);
         if (tc::elect_one()) {
-          if (s2 == 0) {
-            tc_issue_l1(nd, a1h, a1l, aones, tD1, 0, mD1);
-            if (nchunk > 1) tc_issue_l1(nd, a1h, a1l, aones, tD1, 1, mD1);
-          } else {
-            const int c = s2 - 1;
-            tc_issue_l2(nd, tD1, tD2, c);
-            if (c + 2 < nchunk) {
-              tc::mma_commit(mL2);
-              TC_TRACE(13);
-              tc::mbar_wait(mL2, ph2); ph2 ^= 1;                            // A2(c) consumed -> D1[c & 1] reusable
-              tc::fence_after_sync();
-              tc_issue_l1(nd, a1h, a1l, aones, tD1, c + 2, mD1);
-            } else if (c + 1 == nchunk) {
+          if (c >= 0) tc_issue_l2(nd, tD1, tD2, c);
+          const bool chunk_done = c < 0 || (c & 1) || c + 1 == nchunk;    // last block of its chunk
+          if (chunk_done) {
+            const int cn = c < 0 ? 0 : ((c | 1) + 1);                      // first block of the next chunk
+            if (cn < nchunk) {
+              if (c >= 0) {
+                tc::mma_commit(mL2);
+                TC_TRACE(13);
+                tc::mbar_wait(mL2, ph2); ph2 ^= 1;                          // the chunk's A operand consumed -> D1 reusable
+                tc::fence_after_sync();
+              }
+              tc_issue_l1(nd, a1h, a1l, aones, tD1, cn, nchunk - cn < 2 ? nchunk - cn : 2, mD1);
+            } else {
               tc::mma_commit(mDone);
             }
           }
