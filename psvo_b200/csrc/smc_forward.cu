@@ -689,7 +689,8 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   // guide table of the inverse-CDF search (K + 1 ints, K = 2^kbits >= N) when it fits and the search is long enough to pay
   int kbits = 0, guide_off = 0;
   while ((1 << kbits) < N) ++kbits;
-  if (N >= 256 && kbits <= 24 && smem + ((size_t)(1 << kbits) + 1) * sizeof(int) + 16 <= 220 * 1024) {
+  // (every CTA of a sequence builds the whole table: with more than two CTAs per sequence it costs what it saves)
+  if (N >= 256 && parts <= 2 && kbits <= 24 && smem + ((size_t)(1 << kbits) + 1) * sizeof(int) + 16 <= 220 * 1024) {
     guide_off = (int)((smem + 15) & ~(size_t)15);
     smem = (size_t)guide_off + ((size_t)(1 << kbits) + 1) * sizeof(int);
   }
