@@ -148,6 +148,9 @@ CONFIGS = [
     ("c5_sweep", 16, 32, 32, 32, [256], 4096, 2, 3, O.Flags()),
     ("c5_sweep_tensor_core", 16, 32, 32, 32, [256], 4096, 4, 3, O.Flags()),        # large enough for the tcgen05 path
     ("tensor_core_ragged", 5, 7, 6, 9, [128], 3000, 6, 3, O.Flags()),              # tcgen05 path, padded dims, ragged N
+    # enough sequences for one resampling CTA per sequence: guide-table inverse-CDF search + ancestor gather fused into
+    # the next propagate launch (the production configuration of BASELINE config 5)
+    ("tensor_core_guided_resample", 16, 32, 32, 32, [128], 4096, 80, 2, O.Flags()),
     ("tensor_core_poisson", 4, 1, 8, 8, [160], 2048, 8, 3, O.Flags(poisson_emission=True)),
     ("ragged_n", 5, 7, 6, 9, [24], 777, 3, 4, O.Flags()),
     ("single_particle", 2, 1, 1, 1, [8], 1, 2, 4, O.Flags()),
