@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     C[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
     C[48 + d] = 1.0f / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
   }
-  if (tid >= 32 && tid < 64) C[64 + tid - 32] = 1.0f / a.sig[SIG_G * 32 + tid - 32];
+  if (tid >= 32 && tid < 64) C[64 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
   if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
   if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
     const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
@@ -602,12 +602,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
 
+    uint32_t tile_it = 0;
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const int b = wi / tiles_per_seq;
       const long long c = (long long)(wi - b * tiles_per_seq) * 128 + gt;
       const bool live = c < ncand;
       const int i = live ? (int)(c / M) : 0, m = live ? (int)(c - (long long)i * M) : 0;
       const size_t bt = (size_t)b * T + t;
+
+      // ---- per-sequence rows every candidate of the tile shares (proposal mean part, observation): one global load per
+      //      thread into the group's double-buffered slot instead of dependent broadcast loads per element
+      const float* rc = reinterpret_cast<const float*>(sm + L.rowc) + (grp * 2 + (tile_it & 1)) * 64;
+      {
+        float rowv = 0.0f;
+        if (gt < Dx) rowv = last ? __ldg(a.mu_init_all + bt * Dx + gt) : __ldg(a.m2_all + bt * Dx + gt);
+        if (gt >= 32 && gt < 32 + Dy) rowv = __ldg(a.obs + bt * Dy + gt - 32);
+        float* rcw = const_cast<float*>(rc);
+        if (gt < 16) rcw[gt] = rowv;
+        if (gt >= 32 && gt < 64) rcw[16 + gt - 32] = rowv;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      }
+      ++tile_it;
 
       // ---- candidate x~ = mean + sp * eps  (same arithmetic as ffbsi_step_kernel)
       float x[16];
@@ -630,9 +645,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
           float xv = 0.0f;
           if (d < Dx) {
             float mean;
-            if (last) mean = __ldg(a.mu_init_all + bt * Dx + d);
+            if (last) mean = rc[d];
             else {
-              const float m1 = __ldg(a.mu1i + ((size_t)b * N + i) * Dx + d), m2 = __ldg(a.m2_all + bt * Dx + d);
+              const float m1 = __ldg(a.mu1i + ((size_t)b * N + i) * Dx + d), m2 = rc[d];
               mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
             }
             xv = mean + sp[d] * e[k];
@@ -668,14 +683,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
         float mug[16], mgb[16];
         tc::tmem_ld16(g.tD2 + c0, mug);
         tc::tmem_ld16(g.tD2 + NPG + c0, mgb);
+        if (!poisson) {                                                    // branch-free Gaussian emission; columns beyond Dy: y = b2 = 0
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int d = c0 + k;
-          if (d < Dy) {
-            const float y = __ldg(a.obs + bt * Dy + d);
+          for (int k = 0; k < 16; ++k) {
+            const int d = c0 + k;
             const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
-            const float z = poisson ? y - (softplus(mu) + 1e-6f) : (y - mu) * inv_sg[d];
+            const float z = (rc[16 + d] - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int d = c0 + k;
+            if (d < Dy) {
+              const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
+              const float z = rc[16 + d] - (softplus(mu) + 1e-6f);
+              gsum = fmaf(z, z, gsum);
+            }
           }
         }
       }
