@@ -268,6 +268,17 @@ def run_ours(args, w, rank, world, local_rank):
                  "kernel_share_of_step": {"smc_propagate": kms[0] / max(sum(kms), 1e-9), "smc_resample": kms[1] / max(sum(kms), 1e-9),
                                           "mlp_rows": kms[2] / max(sum(kms), 1e-9)},
                  "hbm_frac_whole_step": (bytes_ps * B * N * T / (step_ms * 1e-3) / 1e9) / peaks["hbm_gbs"]})
+    H = w["H"]
+    if kl[0] > 1 and len(H) == 1 and H[0] >= 128 and H[0] % 32 == 0 and Dx <= 16 and w["Dy"] <= 32 and not w.get("poisson", False):
+        # tensor-core propagate kernel: what the tcgen05 pipe is actually busy with.  One M=128, K=16 instruction occupies the
+        # pipe for 40 / 48 cycles at N <= 32 / N = 64 whatever its FLOP (profiles/microbench, elect.sync issue), so the fp16x3
+        # MLPs of a 128-particle tile cost `cyc` pipe cycles although their algorithmic FLOP would need far fewer.
+        nblk = H[0] // 32
+        l1 = (nblk // 2) * 4 * 48 + (nblk % 2) * 4 * 40              # layer 1: 4 MMAs per 64-wide (or trailing 32-wide) chunk
+        cyc = 2 * l1 + nblk * 2 * (40 + 40) + nblk * 2 * (48 + 40)   # + layer 2 of q1 (N = 32, 16) and of g (N = 64, 32), 2 K-steps per block
+        tiles_per_sm = B * ((N + 127) // 128) / 148.0
+        roof["tensor_pipe"] = {"pipe_cycles_per_tile": cyc, "occupancy": tiles_per_sm * cyc / (prop_ms_avg * 1e-3 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6),
+                               "note": "instruction-time occupancy of the tcgen05 pipe (min 40 cycles per M128 K16 MMA); frac above counts algorithmic fp32 FLOP against the dense bf16 peak"}
     line = {
         "metric": "particle-steps/sec (SMC forward filter)", "value": psteps / (step_ms * 1e-3), "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
