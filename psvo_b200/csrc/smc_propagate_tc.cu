@@ -50,17 +50,30 @@ extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_trace(long l
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 32;           // hidden units per pipeline stage
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
-constexpr int kTcBars = 8;             // mbarriers per group (5 used)
+constexpr int kTcBars = 8;             // mbarriers per group (7 used)
 // exact power-of-two operand scales: W1 (and its bias) by 2^4, W2 by 2^8 -> their fp16 lo halves stay normal; the hidden
 // activations travel in 16x units (|h| < 4094) and the layer-2 accumulator in 4096x units, undone in the output FFMA
 constexpr float kW1Scale = 16.0f, kW2Scale = 256.0f, kWUnscale = 1.0f / (16.0f * 256.0f);
 
+// Tensor-memory columns of one group (128 of the CTA's 512):
+//   [0,32)    D2   layer-2 accumulator (q: 16 columns used, g: up to 32)
+//   [32,48)   A1   the network's input row as the layer-1 A operand: fp16 hi (8 columns, two K-elements each) | lo (8 columns)
+//   [48,56)   ones the A operand of the bias MMA: k = 0,1 -> 1, rest 0 (written once per launch)
+//   [64,128)  D1   two layer-1 accumulators of 32 hidden units; the compute threads turn each IN PLACE into the layer-2
+//                  A operand: columns [0,16) fp16 hi (two hidden units per column), [16,32) fp16 lo
+constexpr uint32_t kColD2 = 0, kColA1 = 32, kColOnes = 48, kColD1 = 64;
+// mbarriers of one group
+enum { kBarA1 = 0, kBarD1 = 1 /* +buf */, kBarFull = 3 /* +buf */, kBarL2 = 5, kBarDone = 6 };
+// 1: the MMA thread waits for L2(c) to complete before L1(c+2) overwrites the accumulator L2(c) read its A operand from;
+// 0: relies on the tensor pipe executing one thread's tcgen05.mma in issue order
+#ifndef PSVO_TC_WAR_WAIT
+#define PSVO_TC_WAR_WAIT 1
+#endif
+
 struct TcPropSmem {
-  uint32_t w1q_hi, w1q_lo, w2q, w1g_hi, w1g_lo, w2g;   // fp16 weights (B operands); w2*: [K-group][hi rows | lo rows]
-  uint32_t w1q_b, w1g_b;                               // layer-1 bias as a B operand [H x K=16]: k=0 b_hi, k=1 b_lo
-  uint32_t a_ones;                                     // its A operand [128 x K=16]: k=0,1 = 1 (same for every row)
-  uint32_t b1q, b2q, b1g, b2g, consts;                                        // fp32
-  uint32_t a1_hi[kTcGroups], a1_lo[kTcGroups];        // layer-1 A operands; the layer-2 A operand lives in tensor memory
+  uint32_t w1q_hi, w1q_lo, w1q_b, w2q_hi, w2q_lo;      // fp16 B operands of MLP q1 (f in the FFBSi candidate kernel)
+  uint32_t w1g_hi, w1g_lo, w1g_b, w2g_hi, w2g_lo;      // ... of MLP g
+  uint32_t b2q, b2g, consts;                           // fp32 output biases; per-launch constants (not part of the image)
   uint32_t rowc;                                       // per group, two tile parities: [mu2 (16) | obs (32) | pad] fp32
   uint32_t bars, slot, total;
 };
@@ -69,35 +82,26 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   TcPropSmem s;
   uint32_t o = 0;
 #define PSVO_TAKE(bytes) (o += (((bytes) + 127u) & ~127u), o - (((bytes) + 127u) & ~127u))
-  s.w1q_hi = PSVO_TAKE(H * 16 * 2); s.w1q_lo = PSVO_TAKE(H * 16 * 2);
-  s.w2q = PSVO_TAKE(2 * 16 * H * 2);
-  s.w1g_hi = PSVO_TAKE(H * 16 * 2); s.w1g_lo = PSVO_TAKE(H * 16 * 2);
-  s.w2g = PSVO_TAKE(2 * NPG * H * 2);
-  s.w1q_b = PSVO_TAKE(H * 16 * 2); s.w1g_b = PSVO_TAKE(H * 16 * 2);
-  s.b1q = PSVO_TAKE(H * 4); s.b2q = PSVO_TAKE(16 * 4); s.b1g = PSVO_TAKE(H * 4); s.b2g = PSVO_TAKE(32 * 4);
+  s.w1q_hi = PSVO_TAKE(H * 16 * 2); s.w1q_lo = PSVO_TAKE(H * 16 * 2); s.w1q_b = PSVO_TAKE(H * 16 * 2);
+  s.w2q_hi = PSVO_TAKE(16 * H * 2); s.w2q_lo = PSVO_TAKE(16 * H * 2);
+  s.w1g_hi = PSVO_TAKE(H * 16 * 2); s.w1g_lo = PSVO_TAKE(H * 16 * 2); s.w1g_b = PSVO_TAKE(H * 16 * 2);
+  s.w2g_hi = PSVO_TAKE(NPG * H * 2); s.w2g_lo = PSVO_TAKE(NPG * H * 2);
+  s.b2q = PSVO_TAKE(16 * 4); s.b2g = PSVO_TAKE(32 * 4);
   s.consts = PSVO_TAKE(160 * 4);
-  for (int g = 0; g < kTcGroups; ++g) {
-    s.a1_hi[g] = PSVO_TAKE(128 * 16 * 2); s.a1_lo[g] = PSVO_TAKE(128 * 16 * 2);
-  }
-  s.a_ones = PSVO_TAKE(128 * 16 * 2);
   s.rowc = PSVO_TAKE(kTcGroups * 2 * 64 * 4);
-  s.bars = PSVO_TAKE(kTcBars * kTcGroups * 8); s.slot = PSVO_TAKE(16);   // per group: full[0], mD1[0], mD1[1], mL2, mDone, full[1]
+  s.bars = PSVO_TAKE(kTcBars * kTcGroups * 8); s.slot = PSVO_TAKE(16);
 #undef PSVO_TAKE
   s.total = o;
   return s;
 }
 
-struct TcNetDesc { uint64_t w1h, w1l, w1b, w2; uint32_t idesc2a, idesc2b; int NP; };
+struct TcNetDesc { uint64_t w1h, w1l, w1b, w2h, w2l; uint32_t idesc2; int NP; };
 
 struct TcGroup {
-  unsigned char *pa1h, *pa1l;      // this thread's 16-byte slot in the A1 operand (K-group 0)
-  uint64_t *full, *mD1, *mDone;    // full[0], full[5]: operand staged (128 arrivals, alternating) ; mD1: L1 into D1 done ; mDone: last L2 done
-  uint32_t par;                    // parities of the next completions: bit 0 = mD1, bit 2 = mDone
-  uint32_t k;                      // arrivals so far: arrival k goes to full[(k & 1) * 5]
-  uint32_t tD1, tD2;               // TMEM addresses incl. this warp's lane offset: D1 = 64 columns (one chunk) ; D2 = 2*NP columns
+  uint64_t* bar;                   // the group's mbarriers (kBar*)
+  uint32_t par;                    // parities of the next completions this thread waits for: bit buf = mD1[buf], bit 2 = mDone
+  uint32_t tb;                     // TMEM address of the group's column 0 incl. this warp's lane offset
 };
-
-__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 template <int BIT>
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
@@ -105,132 +109,132 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
   par ^= 1u << BIT;
 }
 
-// "operand staged" arrivals alternate between two mbarriers.  The compute threads may run one stage ahead of the MMA warp
-// (arrival k only proves that stage k-2 was consumed: L1(c) is issued at stage c-1), and two completions of ONE mbarrier
-// before the consumer's parity test would be indistinguishable from none.
-__device__ __forceinline__ void tc_arrive(TcGroup& g) {
-  tc::mbar_arrive(g.full + (g.k & 1u) * 5u);
-  ++g.k;
+// ReLU + fp16 hi/lo split of one pair: hi = fp16(x) toward zero (ReLU inside the packing conversion), lo = fp16(x - hi) with the
+// two subtractions in ONE packed fp32x2 instruction.  x < 0: hi = 0, x - hi < 0 -> lo = 0.  Five instructions per pair, two of
+// them (the packing conversions) on the half-rate ALU pipe -- measured cheapest of the variants in profiles/microbench/r2_pipe_bench.cu.
+__device__ __forceinline__ void split_pair_relu(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = tc::pack_relu_rz(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(hf.x), "f"(hf.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  float l0, l1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(l1) : "l"(d));
+  lo = tc::pack_relu_rn(l0, l1);
 }
 
-// hidden-layer chunk (up to 64 hidden units = `halves` blocks of 32 TMEM columns, ONE layer-1 accumulator): per block
-// TMEM row -> ReLU -> fp16 hi/lo -> back into the SAME 32 columns as the layer-2 A operand (columns 0-15: hi, two hidden
-// units per column; 16-31: lo) -> arrive, so layer 2 of the first block runs while the second is being converted.
-// The activations never touch shared memory: no st.shared, no generic->async proxy fence.
-__device__ __forceinline__ void tc_chunk(TcGroup& g, int halves) {
+// one hidden-layer stage (32 hidden units) of the compute threads: wait for L1 into D1[BUF] -> TMEM row -> ReLU -> fp16 hi/lo ->
+// back into the SAME 32 columns as the layer-2 A operand -> arrive.  The activations never touch shared memory.
+template <int BUF>
+__device__ __forceinline__ void tc_stage(TcGroup& g) {
   TC_TRACE(1);
-  tc_wait<0>(g.mD1, g.par);                                               // L1 of the chunk complete
+  tc_wait<BUF>(g.bar + kBarD1 + BUF, g.par);                               // L1 of the stage complete
   tc::fence_after_sync();
   TC_TRACE(2);
+  uint32_t v[32], r[32];
+  tc::tmem_ld32_issue(g.tb + kColD1 + BUF * 32, v);
+  tc::tmem_ld32_wait(v);
 #pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    if (hb < halves) {
-      float v[32];
-      tc::tmem_ld32(g.tD1 + hb * 32, v);
-      uint32_t r[32];
-#pragma unroll
-      for (int kg = 0; kg < 4; ++kg) {
-        float h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = v[kg * 8 + i];                  // D1 = 16 (W1^T x + b1): the bias rode in the MMA
-        uint4 hi, lo;
-        tc::split8_relu_f16(h, hi, lo);                                    // ReLU inside the packing conversion
-        r[4 * kg] = hi.x; r[4 * kg + 1] = hi.y; r[4 * kg + 2] = hi.z; r[4 * kg + 3] = hi.w;
-        r[16 + 4 * kg] = lo.x; r[16 + 4 * kg + 1] = lo.y; r[16 + 4 * kg + 2] = lo.z; r[16 + 4 * kg + 3] = lo.w;
-      }
-      tc::tmem_st32(g.tD1 + hb * 32, r);
-      tc::tmem_st_wait();
-      tc::fence_before_sync();
-      tc_arrive(g);                                                        // A2 block staged in D1
-    }
-  }
+  for (int j = 0; j < 16; ++j)                                             // D1 = 16 (W1^T x + b1): the bias rode in the MMA
+    split_pair_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), r[j], r[16 + j]);
+  tc::tmem_st32(g.tb + kColD1 + BUF * 32, r);
+  tc::tmem_st_wait();
+  tc::fence_before_sync();
+  tc::mbar_arrive(g.bar + kBarFull + BUF);                                 // A2 stage in place
   TC_TRACE(6);
 }
 
-// compute-group side of one network: x = this thread's input row.  On return the accumulator D2 (2*NP columns:
-// [hi*hi + lo*hi | hi*lo]) is complete; (D2[:, :NP] + D2[:, NP:]) * kWUnscale = W2^T relu(W1^T x + b1).
+// compute-group side of one network: x = this thread's input row.  On return the accumulator D2 is complete:
+// D2 * kWUnscale = W2^T relu(W1^T x + b1).
 __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], int nchunk) {
+  {
+    uint32_t r[16];
 #pragma unroll
-  for (int kg = 0; kg < 2; ++kg) {
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = x[kg * 8 + i];
-    uint4 hi, lo;
-    tc::split8_f16(v, hi, lo);
-    *reinterpret_cast<uint4*>(g.pa1h + kg * 2048) = hi;
-    *reinterpret_cast<uint4*>(g.pa1l + kg * 2048) = lo;
+    for (int j = 0; j < 8; ++j) {
+      const __half2 hh = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+      r[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      r[8 + j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    tc::tmem_st16(g.tb + kColA1, r);
+    tc::tmem_st_wait();
   }
-  tc::fence_proxy_async();
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
-  tc_arrive(g);
-  for (int c = 0; c < nchunk; c += 2) tc_chunk(g, nchunk - c < 2 ? nchunk - c : 2);   // nchunk counts blocks of 32 hidden units
-  tc_wait<2>(g.mDone, g.par);                                              // L2(last) complete
+  tc::mbar_arrive(g.bar + kBarA1);
+  int c = 0;
+  for (; c + 1 < nchunk; c += 2) { tc_stage<0>(g); tc_stage<1>(g); }
+  if (c < nchunk) tc_stage<0>(g);
+  tc_wait<2>(g.bar + kBarDone, g.par);                                     // L2(last) complete
   tc::fence_after_sync();
 }
 
-// MMA-warp side (one elected lane): L1 of the chunk starting at block c (c even; `halves` blocks of 32 hidden units) -> D1.
-// One N = 64 instruction costs 48 tensor-pipe cycles against 2 x 40 for two N = 32 ones (profiles/microbench).
-__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint64_t a1h, uint64_t a1l, uint64_t aones, uint32_t tD1, int c, int halves,
-                                            uint64_t* mD1) {
-  const uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk * halves);
+// MMA-warp side (one elected lane): L1 of stage c -> D1 buffer `tD1` (4 TS-form MMAs, N = 32: x_hi W_hi + x_hi W_lo + x_lo W_hi + bias)
+__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint32_t tA1, uint32_t tD1, int c, uint64_t* mD1) {
+  constexpr uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
   const uint64_t off = (uint64_t)(c * (kTcChunk * 16 / 16));
-  tc::mma_bf16(tD1, a1h, nd.w1h + off, idesc1, false);
-  tc::mma_bf16(tD1, a1h, nd.w1l + off, idesc1, true);
-  tc::mma_bf16(tD1, a1l, nd.w1h + off, idesc1, true);
-  tc::mma_bf16(tD1, aones, nd.w1b + off, idesc1, true);                    // + 16 b1 (hi + lo)
+  tc::mma_f16_ts(tD1, tA1, nd.w1h + off, idesc1, false);
+  tc::mma_f16_ts(tD1, tA1, nd.w1l + off, idesc1, true);
+  tc::mma_f16_ts(tD1, tA1 + 8, nd.w1h + off, idesc1, true);
+  tc::mma_f16_ts(tD1, tA1 + 16, nd.w1b + off, idesc1, true);              // + 16 b1 (hi + lo); A = the ones columns
   tc::mma_commit(mD1);
 }
-// L2 of block c (32 hidden units), A operand in TMEM (D1 columns [32 (c & 1), +32)): per K-step  a_hi x [w_hi ; w_lo] (N = 2 NP)
-// and  a_lo x w_hi (N = NP)
+// L2 of stage c, A operand in TMEM (the converted D1 buffer): per K-step  a_hi w_hi + a_hi w_lo + a_lo w_hi  into D2 (N = NP).
+// A TS-form MMA occupies the tensor pipe for N/2 cycles (profiles/microbench/r2_pipe_bench.cu), so three N = NP instructions cost
+// what the N-stacked pair of round 1 did and the accumulator needs no add of two halves.
 __device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint32_t tD1, uint32_t tD2, int c) {
-  const uint32_t a = tD1 + (c & 1) * 32;
 #pragma unroll
   for (int ks = 0; ks < kTcChunk / 16; ++ks) {
-    const uint64_t b = nd.w2 + (uint64_t)((uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)(2 * nd.NP));   // (2*NP*16 B per K-group) >> 4
-    tc::mma_f16_ts(tD2, a + 8 * ks, b, nd.idesc2a, (c > 0) || (ks > 0));
-    tc::mma_f16_ts(tD2, a + 16 + 8 * ks, b, nd.idesc2b, true);
+    const uint64_t off = (uint64_t)((uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)nd.NP);   // (NP*16 B per K-group) >> 4
+    tc::mma_f16_ts(tD2, tD1 + 8 * ks, nd.w2h + off, nd.idesc2, (c > 0) || (ks > 0));
+    tc::mma_f16_ts(tD2, tD1 + 8 * ks, nd.w2l + off, nd.idesc2, true);
+    tc::mma_f16_ts(tD2, tD1 + 16 + 8 * ks, nd.w2h + off, nd.idesc2, true);
   }
 }
 
-// MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1) the
-// schedule  L1(chunk 0) | L2(block c) per staged block, and after the chunk's last block L1(next chunk)  driven by the
-// group's "operand staged" barriers.  L1 of the next chunk overwrites the columns the chunk's L2s read their A operand from,
-// so it is issued only after they have completed (mL2); the other three groups keep the tensor pipe busy meanwhile.
-__device__ __forceinline__ void tc_mma_warp(unsigned char* sm, const TcPropSmem& L, uint32_t tmem, uint64_t* bars, int grp, int lane,
-                                            int work, int nchunk, int first_net, const TcNetDesc& nq, const TcNetDesc& ng) {
-  (void)lane;
-  uint64_t* full = bars + kTcBars * grp; uint64_t* mD1 = full + 1; uint64_t* mL2 = full + 3; uint64_t* mDone = full + 4;
-  const uint64_t a1h = tc::make_desc(tc::smem_u32(sm + L.a1_hi[grp]), 2048, 128), a1l = tc::make_desc(tc::smem_u32(sm + L.a1_lo[grp]), 2048, 128);
-  const uint64_t aones = tc::make_desc(tc::smem_u32(sm + L.a_ones), 2048, 128);
-  const uint32_t tD1 = tmem + grp * 128, tD2 = tmem + grp * 128 + 64;
-  uint32_t k = 0, ph2 = 0;
+// MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1)
+//   wait A1 -> L1(0), L1(1) ; per stage c: wait "stage c converted" -> L2(c) -> L1(c+2) into the buffer L2(c) just read
+// so layer 1 runs two stages ahead of the conversion and the compute threads find their next accumulator ready.
+__device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint64_t* bars, int grp, int work, int nchunk, int first_net,
+                                            const TcNetDesc& nq, const TcNetDesc& ng) {
+  uint64_t* B = bars + kTcBars * grp;
+  const uint32_t tb = tmem + grp * 128;
+  uint32_t par = 0;                                                        // bit 0: A1, bits 1,2: full[0,1], bit 3: L2
   for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
     for (int net = first_net; net < 2; ++net) {
       const TcNetDesc& nd = net ? ng : nq;
-      for (int c = -1; c < nchunk; ++c) {                                  // c = -1: the network's input operand A1 is staged
-        TC_TRACE(10);
-        tc::mbar_wait(full + (k & 1u) * 5u, (k >> 1) & 1u); ++k;
+      TC_TRACE(10);
+      tc_wait<0>(B + kBarA1, par);
+      tc::fence_after_sync();
+      TC_TRACE(11);
+      if (tc::elect_one()) {
+        tc_issue_l1(nd, tb + kColA1, tb + kColD1, 0, B + kBarD1);
+        if (nchunk > 1) tc_issue_l1(nd, tb + kColA1, tb + kColD1 + 32, 1, B + kBarD1 + 1);
+      }
+      __syncwarp();
+      for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        tc::mbar_wait(B + kBarFull + buf, (par >> (1 + buf)) & 1u); par ^= 2u << buf;
         tc::fence_after_sync();
-        TC_TRACE(11);
+        TC_TRACE(12);
         if (tc::elect_one()) {
-          if (c >= 0) tc_issue_l2(nd, tD1, tD2, c);
-          const bool chunk_done = c < 0 || (c & 1) || c + 1 == nchunk;    // last block of its chunk
-          if (chunk_done) {
-            const int cn = c < 0 ? 0 : ((c | 1) + 1);                      // first block of the next chunk
-            if (cn < nchunk) {
-              if (c >= 0) {
-                tc::mma_commit(mL2);
-                TC_TRACE(13);
-                tc::mbar_wait(mL2, ph2); ph2 ^= 1;                          // the chunk's A operand consumed -> D1 reusable
-                tc::fence_after_sync();
-              }
-              tc_issue_l1(nd, a1h, a1l, aones, tD1, cn, nchunk - cn < 2 ? nchunk - cn : 2, mD1);
-            } else {
-              tc::mma_commit(mDone);
-            }
+          tc_issue_l2(nd, tb + kColD1 + buf * 32, tb + kColD2, c);
+          if (c + 2 < nchunk) {
+#if PSVO_TC_WAR_WAIT
+            tc::mma_commit(B + kBarL2);
+            tc::mbar_wait(B + kBarL2, (par >> 3) & 1u);                    // the stage's A operand consumed -> its D1 buffer reusable
+            tc::fence_after_sync();
+#endif
+            tc_issue_l1(nd, tb + kColA1, tb + kColD1 + buf * 32, c + 2, B + kBarD1 + buf);
+          } else if (c + 1 == nchunk) {
+            tc::mma_commit(B + kBarDone);
           }
         }
-        TC_TRACE(12);
+#if PSVO_TC_WAR_WAIT
+        if (c + 2 < nchunk) par ^= 8u;
+#endif
+        TC_TRACE(13);
         __syncwarp();
       }
     }
@@ -246,9 +250,9 @@ __global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigne
   for (uint32_t i = tid; i < L.consts / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(img)[i] = 0u;
   __syncthreads();
   tc::stage_weight_f16x2(a.q1.W[0], Dx, H, 16, H, kW1Scale, img + L.w1q_hi, img + L.w1q_lo);
-  tc::stage_weight_f16x2_stacked(a.q1.W[1], H, Dx, H, 16, kW2Scale, img + L.w2q);
+  tc::stage_weight_f16x2(a.q1.W[1], H, Dx, H, 16, kW2Scale, img + L.w2q_hi, img + L.w2q_lo);
   tc::stage_weight_f16x2(a.g.W[0], Dx, H, 16, H, kW1Scale, img + L.w1g_hi, img + L.w1g_lo);
-  tc::stage_weight_f16x2_stacked(a.g.W[1], H, Dy, H, NPG, kW2Scale, img + L.w2g);
+  tc::stage_weight_f16x2(a.g.W[1], H, Dy, H, NPG, kW2Scale, img + L.w2g_hi, img + L.w2g_lo);
   // layer-1 biases as B operands: row n of K-group 0 = [fp16(16 b), fp16(16 b - hi), 0 ...]; K-group 1 stays zero
   for (int n = tid; n < H; n += blockDim.x) {
     const float bq = __ldg(a.q1.b[0] + n) * kW1Scale, bg = __ldg(a.g.b[0] + n) * kW1Scale;
@@ -258,11 +262,58 @@ __global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigne
     *reinterpret_cast<__half2*>(img + L.w1q_b + (size_t)n * 16) = q2;
     *reinterpret_cast<__half2*>(img + L.w1g_b + (size_t)n * 16) = g2;
   }
-  float* b1q = reinterpret_cast<float*>(img + L.b1q); float* b2q = reinterpret_cast<float*>(img + L.b2q);
-  float* b1g = reinterpret_cast<float*>(img + L.b1g); float* b2g = reinterpret_cast<float*>(img + L.b2g);
-  for (int i = tid; i < H; i += blockDim.x) { b1q[i] = __ldg(a.q1.b[0] + i); b1g[i] = __ldg(a.g.b[0] + i); }
+  float* b2q = reinterpret_cast<float*>(img + L.b2q);
+  float* b2g = reinterpret_cast<float*>(img + L.b2g);
   for (int i = tid; i < 16; i += blockDim.x) b2q[i] = i < Dx ? __ldg(a.q1.b[1] + i) : 0.0f;
   for (int i = tid; i < 32; i += blockDim.x) b2g[i] = i < Dy ? __ldg(a.g.b[1] + i) : 0.0f;
+}
+
+// ---- common prologue of the three kernels that run the pipeline -------------------------------------------------------
+struct TcCtx { uint32_t tmem; uint64_t* bars; TcNetDesc nq, ng; };
+
+// part 1 (before the kernel's own constant staging): weight image -> shared memory (one coalesced copy of what
+// tc_stage_image_kernel prepared once per pass), mbarrier init, TMEM allocation
+__device__ __forceinline__ void tc_setup_begin(unsigned char* sm, const TcPropSmem& L, const unsigned char* __restrict__ image, int tid, int warp) {
+  const uint4* src = reinterpret_cast<const uint4*>(image);
+  uint4* dst = reinterpret_cast<uint4*>(sm);
+  const int n16 = (int)(L.consts / 16);
+#pragma unroll 4
+  for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  if (tid < kTcBars * kTcGroups) {
+    const int k = tid % kTcBars;
+    tc::mbar_init(bars + tid, (k == kBarA1 || k == kBarFull || k == kBarFull + 1) ? 128 : 1);
+  }
+  if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(sm + L.slot), 512);
+}
+// part 2: publish (generic -> async proxy for the staged weights, barrier init, TMEM address), build the operand descriptors
+template <int NPG>
+__device__ __forceinline__ void tc_setup_finish(unsigned char* sm, const TcPropSmem& L, int H, TcCtx& cx) {
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  cx.tmem = *reinterpret_cast<uint32_t*>(sm + L.slot);
+  cx.bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+  TcNetDesc& nq = cx.nq; TcNetDesc& ng = cx.ng;
+  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
+  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
+  nq.w2h = tc::make_desc(tc::smem_u32(sm + L.w2q_hi), 16 * 16, 128); nq.w2l = tc::make_desc(tc::smem_u32(sm + L.w2q_lo), 16 * 16, 128);
+  nq.idesc2 = tc::make_idesc_f16(128, 16); nq.NP = 16;
+  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
+  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
+  ng.w2h = tc::make_desc(tc::smem_u32(sm + L.w2g_hi), NPG * 16, 128); ng.w2l = tc::make_desc(tc::smem_u32(sm + L.w2g_lo), NPG * 16, 128);
+  ng.idesc2 = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
+}
+// a compute thread's view of its group; also writes the thread's row of the bias MMA's "ones" operand (published by the
+// thread's first arrival on the A1 barrier)
+__device__ __forceinline__ void tc_group_init(TcGroup& g, const TcCtx& cx, int grp, int warp) {
+  g.bar = cx.bars + kTcBars * grp;
+  g.par = 0;
+  g.tb = cx.tmem + grp * 128 + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};     // half2(1, 1): k = 0 multiplies b_hi, k = 1 b_lo
+  tc::tmem_st8(g.tb + kColOnes, ones);
+  tc::tmem_st_wait();
 }
 
 template <int NPG>
@@ -280,18 +331,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);     // [g][kTcBars]: full, mD1[0], mD1[1], mL2, mDone
-  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
-
-  // ---- weights (fp16 hi/lo, UMMA B layout, pre-scaled) and biases: one coalesced copy of the image that
-  //      tc_stage_image_kernel prepared once for this forward pass
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
-    uint4* dst = reinterpret_cast<uint4*>(sm);
-    const int n16 = (int)(L.consts / 16);
-#pragma unroll 4
-    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
+  tc_setup_begin(sm, L, a.tc_image, tid, warp);
   if (tid < 16) {
     const int d = tid;
     const float s1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d], s2 = a.sig[SIG_Q2 * 32 + d];
@@ -300,17 +340,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
   }
   if (tid >= 32 && tid < 64) C[96 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
-  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
-  if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
-    const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
-    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-  }
   TC_TRACE_INIT();
-  if (warp == 0) tc::tmem_alloc(slot, 512);
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
+  TcCtx tcx;
+  tc_setup_finish<NPG>(sm, L, H, tcx);
   if (tid == 0) {
     float lp = 0.f, lf = 0.f, lg = 0.f;
     for (int d = 0; d < Dx; ++d) { lp += logf(C[16 + d]); lf += logf(C[d]); }
@@ -318,22 +350,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     C[128] = lp; C[129] = lf; C[130] = lg;
   }
   __syncthreads();
-  const uint32_t tmem = *slot;
   const int tiles_per_seq = (N + 127) / 128;
   const int work = a.B * tiles_per_seq;
 
-  TcNetDesc nq, ng;
-  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
-  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
-  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
-  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
-  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
-  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
-
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, t0 ? 1 : 0, nq, ng);
+    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, t0 ? 1 : 0, tcx.nq, tcx.ng);
   } else {
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
@@ -345,10 +366,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
     (void)s1;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
-    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
+    tc_group_init(g, tcx, grp, warp);
 
     uint32_t tile_it = 0;
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
@@ -427,11 +445,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       }
       if (!t0) {
         tc_mlp_compute(g, x, nchunk);
-        float mb[16];
-        tc::tmem_ld16(g.tD2, mu1);
-        tc::tmem_ld16(g.tD2 + 16, mb);
+        tc::tmem_ld16(g.tb + kColD2, mu1);
 #pragma unroll
-        for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d] + mb[d], kWUnscale, sb2q[d]);
+        for (int d = 0; d < 16; ++d) mu1[d] = fmaf(mu1[d], kWUnscale, sb2q[d]);
       } else {
 #pragma unroll
         for (int d = 0; d < 16; ++d) mu1[d] = d < Dx ? __ldg(a.mu0 + (size_t)b * Dx + d) : 0.0f;
@@ -482,14 +498,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       float gsum = 0.f;
 #pragma unroll
       for (int c = 0; c < NPG; c += 16) {
-        float mug[16], mgb[16];
-        tc::tmem_ld16(g.tD2 + c, mug);
-        tc::tmem_ld16(g.tD2 + NPG + c, mgb);
+        float mug[16];
+        tc::tmem_ld16(g.tb + kColD2 + c, mug);
         if (!poisson) {                                                    // branch-free Gaussian emission; columns beyond Dy: y = b2 = 0
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int d = c + i;
-            const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
+            const float mu = fmaf(mug[i], kWUnscale, sb2g[d]);
             const float z = (rc[16 + d] - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
           }
@@ -498,7 +513,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
           for (int i = 0; i < 16; ++i) {
             const int d = c + i;
             if (d < Dy) {
-              const float mu = fmaf(mug[i] + mgb[i], kWUnscale, sb2g[d]);
+              const float mu = fmaf(mug[i], kWUnscale, sb2g[d]);
               const float z = rc[16 + d] - (softplus(mu) + 1e-6f);
               gsum = fmaf(z, z, gsum);
             }
@@ -514,7 +529,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == 0) tc::tmem_dealloc(tcx.tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -538,15 +553,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
   // consts: sp[16] | inv1[16] | inv2[16] | inv_sf[16] | inv_sg[32] | ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
-    uint4* dst = reinterpret_cast<uint4*>(sm);
-    const int n16 = (int)(L.consts / 16);
-#pragma unroll 4
-    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
+  tc_setup_begin(sm, L, a.tc_image, tid, warp);
   if (tid < 16) {
     const int d = tid;
     const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
@@ -555,16 +562,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     C[48 + d] = 1.0f / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
   }
   if (tid >= 32 && tid < 64) C[64 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
-  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
-  if (tid < 256) {                                                            // A operand of the bias MMA: every row [1, 1, 0 ...]
-    const uint32_t one2 = 0x3C003C00u;                                        // half2(1, 1)
-    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (warp == 0) tc::tmem_alloc(slot, 512);
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
+  TcCtx tcx;
+  tc_setup_finish<NPG>(sm, L, H, tcx);
   if (tid == 0) {
     float lf = 0.f, lg = 0.f;
     for (int d = 0; d < Dx; ++d) lf += logf(a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d]);
@@ -572,23 +571,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     C[96] = lf; C[97] = lg;
   }
   __syncthreads();
-  const uint32_t tmem = *slot;
   const long long ncand = (long long)N * M;
   const int tiles_per_seq = (int)((ncand + 127) / 128);
   const int work = a.B * tiles_per_seq;
 
-  TcNetDesc nq, ng;
-  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
-  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
-  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
-  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
-  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
-  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
-
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, last ? 1 : 0, nq, ng);
+    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, last ? 1 : 0, tcx.nq, tcx.ng);
   } else {
     const int grp = warp >> 2;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
@@ -597,10 +585,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
-    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
+    tc_group_init(g, tcx, grp, warp);
 
     uint32_t tile_it = 0;
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
@@ -660,15 +645,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
       float f_lp = 0.0f;
       if (!last) {
         tc_mlp_compute(g, x, nchunk);
-        float muf[16], mb[16];
-        tc::tmem_ld16(g.tD2, muf);
-        tc::tmem_ld16(g.tD2 + 16, mb);
+        float muf[16];
+        tc::tmem_ld16(g.tb + kColD2, muf);
         const float* xn = a.X_next + ((bt + 1) * N + i) * Dx;
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
           if (d < Dx) {
-            const float mu = fmaf(muf[d] + mb[d], kWUnscale, sb2q[d]);
+            const float mu = fmaf(muf[d], kWUnscale, sb2q[d]);
             const float z = (xn[d] - mu) * inv_sf[d];
             s = fmaf(z, z, s);
           }
@@ -680,14 +664,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
       float gsum = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < NPG; c0 += 16) {
-        float mug[16], mgb[16];
-        tc::tmem_ld16(g.tD2 + c0, mug);
-        tc::tmem_ld16(g.tD2 + NPG + c0, mgb);
+        float mug[16];
+        tc::tmem_ld16(g.tb + kColD2 + c0, mug);
         if (!poisson) {                                                    // branch-free Gaussian emission; columns beyond Dy: y = b2 = 0
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int d = c0 + k;
-            const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
+            const float mu = fmaf(mug[k], kWUnscale, sb2g[d]);
             const float z = (rc[16 + d] - mu) * inv_sg[d];
             gsum = fmaf(z, z, gsum);
           }
@@ -696,7 +679,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
           for (int k = 0; k < 16; ++k) {
             const int d = c0 + k;
             if (d < Dy) {
-              const float mu = fmaf(mug[k] + mgb[k], kWUnscale, sb2g[d]);
+              const float mu = fmaf(mug[k], kWUnscale, sb2g[d]);
               const float z = rc[16 + d] - (softplus(mu) + 1e-6f);
               gsum = fmaf(z, z, gsum);
             }
@@ -713,7 +696,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == 0) tc::tmem_dealloc(tcx.tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -731,49 +714,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
   const int nchunk = H / kTcChunk;
   float* sb2q = reinterpret_cast<float*>(sm + L.b2q);
   float* sb2g = reinterpret_cast<float*>(sm + L.b2g);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(sm + L.slot);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.tc_image);
-    uint4* dst = reinterpret_cast<uint4*>(sm);
-    const int n16 = (int)(L.consts / 16);
-#pragma unroll 4
-    for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-  }
-  if (tid < kTcBars * kTcGroups) tc::mbar_init(bars + tid, (tid % kTcBars) == 0 || (tid % kTcBars) == 5 ? 128 : 1);
-  if (tid < 256) {
-    const uint32_t one2 = 0x3C003C00u;
-    *reinterpret_cast<uint4*>(sm + L.a_ones + tid * 16) = tid < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (warp == 0) tc::tmem_alloc(slot, 512);
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = *slot;
+  tc_setup_begin(sm, L, a.tc_image, tid, warp);
+  TcCtx tcx;
+  tc_setup_finish<NPG>(sm, L, H, tcx);
   const long long rows = (long long)a.B * N;
   const int work = (int)((rows + 127) / 128);
 
-  TcNetDesc nq, ng;
-  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
-  nq.w2 = tc::make_desc(tc::smem_u32(sm + L.w2q), 2 * 16 * 16, 128);
-  nq.idesc2a = tc::make_idesc_f16(128, 32); nq.idesc2b = tc::make_idesc_f16(128, 16); nq.NP = 16;
-  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
-  ng.w2 = tc::make_desc(tc::smem_u32(sm + L.w2g), 2 * NPG * 16, 128);
-  ng.idesc2a = tc::make_idesc_f16(128, 2 * NPG); ng.idesc2b = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
-
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(sm, L, tmem, bars, warp - kTcGroups * 4, lane, work, nchunk, with_q ? 0 : 1, nq, ng);
+    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1, tcx.nq, tcx.ng);
   } else {
     const int grp = warp >> 2;
     TcGroup g;
     const int gt = tid & 127;
-    g.full = bars + kTcBars * grp; g.mD1 = g.full + 1; g.mDone = g.full + 4; g.par = 0; g.k = 0;
-    g.pa1h = sm + L.a1_hi[grp] + gt * 16; g.pa1l = sm + L.a1_lo[grp] + gt * 16;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    g.tD1 = tmem + grp * 128 + lane_base; g.tD2 = tmem + grp * 128 + 64 + lane_base;
+    tc_group_init(g, tcx, grp, warp);
     for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
       const long long r = (long long)wi * 128 + gt;
       const bool live = r < rows;
@@ -784,13 +737,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
 #pragma unroll
         for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
         tc_mlp_compute(g, x, nchunk);
-        float mu[16], mb[16];
-        tc::tmem_ld16(g.tD2, mu);
-        tc::tmem_ld16(g.tD2 + 16, mb);
+        float mu[16];
+        tc::tmem_ld16(g.tb + kColD2, mu);
         if (live) {
           float* dst = a.muq + r * Dx;
 #pragma unroll
-          for (int d = 0; d < 16; ++d) if (d < Dx) dst[d] = fmaf(mu[d] + mb[d], kWUnscale, sb2q[d]);
+          for (int d = 0; d < 16; ++d) if (d < Dx) dst[d] = fmaf(mu[d], kWUnscale, sb2q[d]);
         }
       }
       {
@@ -800,13 +752,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
         tc_mlp_compute(g, x, nchunk);
 #pragma unroll
         for (int c0 = 0; c0 < NPG; c0 += 16) {
-          float mu[16], mb[16];
-          tc::tmem_ld16(g.tD2 + c0, mu);
-          tc::tmem_ld16(g.tD2 + NPG + c0, mb);
+          float mu[16];
+          tc::tmem_ld16(g.tb + kColD2 + c0, mu);
           if (live) {
             float* dst = a.mug + r * Dy;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) if (c0 + k < Dy) dst[c0 + k] = fmaf(mu[k] + mb[k], kWUnscale, sb2g[c0 + k]);
+            for (int k = 0; k < 16; ++k) if (c0 + k < Dy) dst[c0 + k] = fmaf(mu[k], kWUnscale, sb2g[c0 + k]);
           }
         }
       }
@@ -814,7 +765,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == 0) tc::tmem_dealloc(tcx.tmem, 512);
 }
 
 int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st) {
