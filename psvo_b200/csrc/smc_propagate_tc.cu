@@ -48,9 +48,10 @@ extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_trace(long l
 #endif
 
 constexpr int kTcGroups = 4;
-constexpr int kTcChunk = 32;           // hidden units per pipeline stage
+constexpr int kTcChunk = 16;           // hidden units per pipeline stage = one K-step of layer 2
+constexpr int kTcBufs = 4;             // layer-1 accumulators per group
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
-constexpr int kTcBars = 8;             // mbarriers per group (7 used)
+constexpr int kTcBars = 12;            // mbarriers per group
 // exact power-of-two operand scales: W1 (and its bias) by 2^4, W2 by 2^8 -> their fp16 lo halves stay normal; the hidden
 // activations travel in 16x units (|h| < 4094) and the layer-2 accumulator in 4096x units, undone in the output FFMA
 constexpr float kW1Scale = 16.0f, kW2Scale = 256.0f, kWUnscale = 1.0f / (16.0f * 256.0f);
@@ -59,15 +60,15 @@ constexpr float kW1Scale = 16.0f, kW2Scale = 256.0f, kWUnscale = 1.0f / (16.0f *
 //   [0,32)    D2   layer-2 accumulator (q: 16 columns used, g: up to 32)
 //   [32,48)   A1   the network's input row as the layer-1 A operand: fp16 hi (8 columns, two K-elements each) | lo (8 columns)
 //   [48,56)   ones the A operand of the bias MMA: k = 0,1 -> 1, rest 0 (written once per launch)
-//   [64,128)  D1   two layer-1 accumulators of 32 hidden units; the compute threads turn each IN PLACE into the layer-2
-//                  A operand: columns [0,16) fp16 hi (two hidden units per column), [16,32) fp16 lo
+//   [64,128)  D1   four layer-1 accumulators of 16 hidden units; the compute threads turn each IN PLACE into the layer-2
+//                  A operand of one K-step: columns [0,8) fp16 hi (two hidden units per column), [8,16) fp16 lo
 constexpr uint32_t kColD2 = 0, kColA1 = 32, kColOnes = 48, kColD1 = 64;
-// mbarriers of one group
-enum { kBarA1 = 0, kBarD1 = 1 /* +buf */, kBarFull = 3 /* +buf */, kBarL2 = 5, kBarDone = 6 };
-// 1: the MMA thread waits for L2(c) to complete before L1(c+2) overwrites the accumulator L2(c) read its A operand from;
-// 0: relies on the tensor pipe executing one thread's tcgen05.mma in issue order
+// mbarriers of one group: A1 staged (128 arrivals) | L1 of a stage complete, per buffer | stage converted (128), per buffer |
+// L2 of a stage complete (only in the PSVO_TC_WAR_WAIT build) | last L2 of the network complete
+enum { kBarA1 = 0, kBarD1 = 1, kBarFull = 5, kBarL2 = 9, kBarDone = 10, kBarImage = 11 /* group 0's slot: weight image landed */ };
+// 1: wait for L2(c) to complete before L1(c+4) overwrites the accumulator it read its A operand from (conservative, slower)
 #ifndef PSVO_TC_WAR_WAIT
-#define PSVO_TC_WAR_WAIT 1
+#define PSVO_TC_WAR_WAIT 0
 #endif
 
 struct TcPropSmem {
@@ -95,18 +96,39 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   return s;
 }
 
-struct TcNetDesc { uint64_t w1h, w1l, w1b, w2h, w2l; uint32_t idesc2; int NP; };
-
 struct TcGroup {
-  uint64_t* bar;                   // the group's mbarriers (kBar*)
-  uint32_t par;                    // parities of the next completions this thread waits for: bit buf = mD1[buf], bit 2 = mDone
+  uint32_t bar;                    // shared-memory address of the group's mbarriers (kBar*, 8 bytes each)
+  uint32_t par;                    // parities of the next completions this thread waits for: bits 0-3 = L1 into buffer 0-3, bit 4 = mDone
   uint32_t tb;                     // TMEM address of the group's column 0 incl. this warp's lane offset
 };
 
-template <int BIT>
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t& par) {
-  tc::mbar_wait(bar, (par >> BIT) & 1u);
-  par ^= 1u << BIT;
+// An opaque copy of a loop-invariant address.  Without it ptxas rematerialises the barrier / TMEM addresses from the kernel
+// parameters at every use (a dependent chain of ~10 uniform-datapath instructions, ~100 cycles, in front of every
+// mbarrier wait and arrive of the stage loop) instead of keeping them in a register.
+__device__ __forceinline__ uint32_t tc_opaque(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}\n"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_wait_bit(uint32_t bar, uint32_t& par, int bit) {
+  mbar_wait_u32(bar, (par >> bit) & 1u);
+  par ^= 1u << bit;
 }
 
 // ReLU + fp16 hi/lo split of one pair: hi = fp16(x) toward zero (ReLU inside the packing conversion), lo = fp16(x - hi) with the
@@ -124,30 +146,41 @@ __device__ __forceinline__ void split_pair_relu(float x0, float x1, uint32_t& hi
   lo = tc::pack_relu_rn(l0, l1);
 }
 
-// one hidden-layer stage (32 hidden units) of the compute threads: wait for L1 into D1[BUF] -> TMEM row -> ReLU -> fp16 hi/lo ->
-// back into the SAME 32 columns as the layer-2 A operand -> arrive.  The activations never touch shared memory.
+// One hidden-layer stage (16 hidden units) of the compute threads, software pipelined:
+//   v  : the stage's accumulator row, its tcgen05.ld issued one stage earlier      -> wait::ld
+//   vn : prefetch of stage c+1 (layer 1 runs three stages ahead, so its accumulator is normally complete)
+//   ReLU + hi/lo split of v in registers; only then publish stage c-1 (its tcgen05.st has long completed: no exposed wait),
+//   and store stage c IN PLACE as the layer-2 A operand of one K-step.  The activations never touch shared memory.
 template <int BUF>
-__device__ __forceinline__ void tc_stage(TcGroup& g) {
+__device__ __forceinline__ void tc_stage(TcGroup& g, int c, int nst, uint32_t (&v)[16], uint32_t (&vn)[16]) {
+  constexpr int NB = (BUF + 1) & (kTcBufs - 1), PB = (BUF + kTcBufs - 1) & (kTcBufs - 1);
   TC_TRACE(1);
-  tc_wait<BUF>(g.bar + kBarD1 + BUF, g.par);                               // L1 of the stage complete
-  tc::fence_after_sync();
+  tc::tmem_ld16_wait(v);
   TC_TRACE(2);
-  uint32_t v[32], r[32];
-  tc::tmem_ld32_issue(g.tb + kColD1 + BUF * 32, v);
-  tc::tmem_ld32_wait(v);
+  if (c + 1 < nst) {
+    mbar_wait_u32(g.bar + 8 * (kBarD1 + NB), (g.par >> NB) & 1u);          // L1 of stage c+1 complete
+    g.par ^= 1u << NB;
+    tc::fence_after_sync();
+    tc::tmem_ld16_issue(g.tb + kColD1 + NB * kTcChunk, vn);
+  }
+  TC_TRACE(3);
+  if (c > 0) {                                                             // publish stage c-1: its tcgen05.st was issued a stage ago
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    mbar_arrive_u32(g.bar + 8 * (kBarFull + PB));
+  }
+  uint32_t r[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)                                             // D1 = 16 (W1^T x + b1): the bias rode in the MMA
-    split_pair_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), r[j], r[16 + j]);
-  tc::tmem_st32(g.tb + kColD1 + BUF * 32, r);
-  tc::tmem_st_wait();
-  tc::fence_before_sync();
-  tc::mbar_arrive(g.bar + kBarFull + BUF);                                 // A2 stage in place
+  for (int j = 0; j < 8; ++j)                                              // D1 = 16 (W1^T x + b1): the bias rode in the MMA
+    split_pair_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), r[j], r[8 + j]);
+  TC_TRACE(4);
+  tc::tmem_st16(g.tb + kColD1 + BUF * kTcChunk, r);
   TC_TRACE(6);
 }
 
 // compute-group side of one network: x = this thread's input row.  On return the accumulator D2 is complete:
-// D2 * kWUnscale = W2^T relu(W1^T x + b1).
-__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], int nchunk) {
+// D2 * kWUnscale = W2^T relu(W1^T x + b1).   nst = H / 16 stages (even).
+__device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16], int nst) {
   {
     uint32_t r[16];
 #pragma unroll
@@ -162,82 +195,127 @@ __device__ __forceinline__ void tc_mlp_compute(TcGroup& g, const float (&x)[16],
     tc::tmem_st_wait();
   }
   tc::fence_before_sync();           // also orders this thread's earlier tcgen05.ld of the previous accumulators
-  tc::mbar_arrive(g.bar + kBarA1);
-  int c = 0;
-  for (; c + 1 < nchunk; c += 2) { tc_stage<0>(g); tc_stage<1>(g); }
-  if (c < nchunk) tc_stage<0>(g);
-  tc_wait<2>(g.bar + kBarDone, g.par);                                     // L2(last) complete
+  mbar_arrive_u32(g.bar + 8 * kBarA1);
+  uint32_t va[16], vb[16];
+  tc_wait_bit(g.bar + 8 * kBarD1, g.par, 0);                                   // L1 of stage 0 complete
+  tc::fence_after_sync();
+  tc::tmem_ld16_issue(g.tb + kColD1, va);
+#pragma unroll 1
+  for (int c = 0; c < nst; c += 4) {                                       // every network starts in buffer 0: static buffer indices
+    tc_stage<0>(g, c, nst, va, vb);
+    tc_stage<1>(g, c + 1, nst, vb, va);
+    if (c + 2 < nst) {
+      tc_stage<2>(g, c + 2, nst, va, vb);
+      tc_stage<3>(g, c + 3, nst, vb, va);
+    }
+  }
+  tc::tmem_st_wait();
+  tc::fence_before_sync();
+  mbar_arrive_u32(g.bar + 8 * (kBarFull + ((nst - 1) & (kTcBufs - 1))));         // last stage in place
+  tc_wait_bit(g.bar + 8 * kBarDone, g.par, 4);                                 // L2(last) complete
   tc::fence_after_sync();
 }
 
-// MMA-warp side (one elected lane): L1 of stage c -> D1 buffer `tD1` (4 TS-form MMAs, N = 32: x_hi W_hi + x_hi W_lo + x_lo W_hi + bias)
-__device__ __forceinline__ void tc_issue_l1(const TcNetDesc& nd, uint32_t tA1, uint32_t tD1, int c, uint64_t* mD1) {
+// ---- MMA-issuing warp ----------------------------------------------------------------------------------------------
+// Everything the issuing thread touches is derived from warp-uniform values (shared-memory offsets of the layout, the loop
+// counter) so that ptxas keeps descriptors and addresses in uniform registers: one event (wait -> 3 + 4 MMAs -> 2 commits)
+// must cost far less than the conversion of one stage, or layer 1 stops running ahead of the compute threads.
+struct TcNetAddr { uint32_t w1h, w1l, w1b, w2h, w2l; };     // shared-memory byte addresses of the network's B operands
+
+// L1 of stage c -> D1 buffer `tD1` (4 TS-form MMAs, N = 16: x_hi W_hi + x_hi W_lo + x_lo W_hi + bias)
+__device__ __forceinline__ void tc_issue_l1(const TcNetAddr& na, uint32_t lbo1, uint32_t tA1, uint32_t tD1, int c, uint32_t bar_d1) {
   constexpr uint32_t idesc1 = tc::make_idesc_f16(128, kTcChunk);
-  const uint64_t off = (uint64_t)(c * (kTcChunk * 16 / 16));
-  tc::mma_f16_ts(tD1, tA1, nd.w1h + off, idesc1, false);
-  tc::mma_f16_ts(tD1, tA1, nd.w1l + off, idesc1, true);
-  tc::mma_f16_ts(tD1, tA1 + 8, nd.w1h + off, idesc1, true);
-  tc::mma_f16_ts(tD1, tA1 + 16, nd.w1b + off, idesc1, true);              // + 16 b1 (hi + lo); A = the ones columns
-  tc::mma_commit(mD1);
+  const uint32_t off = (uint32_t)c * (kTcChunk * 16);
+  const uint64_t w1h = tc::make_desc(na.w1h + off, lbo1, 128), w1l = tc::make_desc(na.w1l + off, lbo1, 128);
+  const uint64_t w1b = tc::make_desc(na.w1b + off, lbo1, 128);
+  tc::mma_f16_ts(tD1, tA1, w1h, idesc1, false);
+  tc::mma_f16_ts(tD1, tA1, w1l, idesc1, true);
+  tc::mma_f16_ts(tD1, tA1 + 8, w1h, idesc1, true);
+  tc::mma_f16_ts(tD1, tA1 + 16, w1b, idesc1, true);                       // + 16 b1 (hi + lo); A = the ones columns
+  mma_commit_u32(bar_d1);
 }
-// L2 of stage c, A operand in TMEM (the converted D1 buffer): per K-step  a_hi w_hi + a_hi w_lo + a_lo w_hi  into D2 (N = NP).
+// L2 of stage c = K-step c of layer 2, A operand in TMEM (the converted D1 buffer):  a_hi w_hi + a_hi w_lo + a_lo w_hi  into D2.
 // A TS-form MMA occupies the tensor pipe for N/2 cycles (profiles/microbench/r2_pipe_bench.cu), so three N = NP instructions cost
 // what the N-stacked pair of round 1 did and the accumulator needs no add of two halves.
-__device__ __forceinline__ void tc_issue_l2(const TcNetDesc& nd, uint32_t tD1, uint32_t tD2, int c) {
-#pragma unroll
-  for (int ks = 0; ks < kTcChunk / 16; ++ks) {
-    const uint64_t off = (uint64_t)((uint32_t)(c * (kTcChunk / 8) + 2 * ks) * (uint32_t)nd.NP);   // (NP*16 B per K-group) >> 4
-    tc::mma_f16_ts(tD2, tD1 + 8 * ks, nd.w2h + off, nd.idesc2, (c > 0) || (ks > 0));
-    tc::mma_f16_ts(tD2, tD1 + 8 * ks, nd.w2l + off, nd.idesc2, true);
-    tc::mma_f16_ts(tD2, tD1 + 16 + 8 * ks, nd.w2h + off, nd.idesc2, true);
-  }
+template <int NP>
+__device__ __forceinline__ void tc_issue_l2(const TcNetAddr& na, uint32_t tD1, uint32_t tD2, int c) {
+  constexpr uint32_t idesc2 = tc::make_idesc_f16(128, NP);
+  const uint32_t off = (uint32_t)(2 * c) * (NP * 16);                     // K-groups 2c, 2c+1
+  const uint64_t w2h = tc::make_desc(na.w2h + off, NP * 16, 128), w2l = tc::make_desc(na.w2l + off, NP * 16, 128);
+  tc::mma_f16_ts(tD2, tD1, w2h, idesc2, c > 0);
+  tc::mma_f16_ts(tD2, tD1, w2l, idesc2, true);
+  tc::mma_f16_ts(tD2, tD1 + 8, w2h, idesc2, true);
 }
 
-// MMA-issuing warp of group `grp` (one elected lane): for every tile of the group and every network (first_net..1)
-//   wait A1 -> L1(0), L1(1) ; per stage c: wait "stage c converted" -> L2(c) -> L1(c+2) into the buffer L2(c) just read
-// so layer 1 runs two stages ahead of the conversion and the compute threads find their next accumulator ready.
-__device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint64_t* bars, int grp, int work, int nchunk, int first_net,
-                                            const TcNetDesc& nq, const TcNetDesc& ng) {
-  uint64_t* B = bars + kTcBars * grp;
-  const uint32_t tb = tmem + grp * 128;
-  uint32_t par = 0;                                                        // bit 0: A1, bits 1,2: full[0,1], bit 3: L2
-  for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
-    for (int net = first_net; net < 2; ++net) {
-      const TcNetDesc& nd = net ? ng : nq;
-      TC_TRACE(10);
-      tc_wait<0>(B + kBarA1, par);
-      tc::fence_after_sync();
-      TC_TRACE(11);
-      if (tc::elect_one()) {
-        tc_issue_l1(nd, tb + kColA1, tb + kColD1, 0, B + kBarD1);
-        if (nchunk > 1) tc_issue_l1(nd, tb + kColA1, tb + kColD1 + 32, 1, B + kBarD1 + 1);
-      }
-      __syncwarp();
-      for (int c = 0; c < nchunk; ++c) {
-        const int buf = c & 1;
-        tc::mbar_wait(B + kBarFull + buf, (par >> (1 + buf)) & 1u); par ^= 2u << buf;
+// one network of one tile:  wait A1 -> L1(0..3) ; per stage c: wait "stage c converted" -> L2(c) -> L1(c+4) into the very buffer
+// L2(c) reads its A operand from.  Layer 1 thus runs four stages ahead of the conversion, which is what it takes to cover the
+// round trip  arrive -> this warp wakes -> issue -> tensor pipe -> commit -> compute threads wake  (~500-600 cycles against
+// ~300 per 16-unit stage), and the compute threads' prefetch finds its accumulator complete.
+// Write-after-read on the D1 buffer: L1(c+4) is issued by this thread right after L2(c) and the tensor pipe executes one
+// thread's tcgen05.mma in issue order (L2(c) has fetched its A operand before L1(c+4) can write the columns); waiting for
+// L2(c)'s completion instead would put ~300 cycles into every one of the 64 events of a tile (PSVO_TC_WAR_WAIT=1 builds that
+// conservative variant; it was the slower one by 25 %).
+// par: bit 0 = A1, bits 1-4 = full[0..3], bit 5 = L2
+template <int NP>
+__device__ __forceinline__ void tc_mma_net(const TcNetAddr& na, uint32_t lbo1, uint32_t tb, uint32_t bars, int nst, uint32_t& par) {
+  TC_TRACE(10);
+  mbar_wait_u32(bars + 8 * kBarA1, par & 1u); par ^= 1u;
+  tc::fence_after_sync();
+  TC_TRACE(11);
+  if (tc::elect_one()) {
+#pragma unroll
+    for (int c = 0; c < kTcBufs; ++c)
+      if (c < nst) tc_issue_l1(na, lbo1, tb + kColA1, tb + kColD1 + c * kTcChunk, c, bars + 8 * (kBarD1 + c));
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int c0 = 0; c0 < nst; c0 += kTcBufs) {
+#pragma unroll
+    for (int buf = 0; buf < kTcBufs; ++buf) {                              // static buffer index: addresses fold into immediates
+      const int c = c0 + buf;
+      if (c < nst) {
+        mbar_wait_u32(bars + 8 * (kBarFull + buf), (par >> (1 + buf)) & 1u); par ^= 2u << buf;
         tc::fence_after_sync();
         TC_TRACE(12);
+        const bool more = c + kTcBufs < nst;
         if (tc::elect_one()) {
-          tc_issue_l2(nd, tb + kColD1 + buf * 32, tb + kColD2, c);
-          if (c + 2 < nchunk) {
+          tc_issue_l2<NP>(na, tb + kColD1 + buf * kTcChunk, tb + kColD2, c);
+          if (more) {
 #if PSVO_TC_WAR_WAIT
-            tc::mma_commit(B + kBarL2);
-            tc::mbar_wait(B + kBarL2, (par >> 3) & 1u);                    // the stage's A operand consumed -> its D1 buffer reusable
+            mma_commit_u32(bars + 8 * kBarL2);
+            mbar_wait_u32(bars + 8 * kBarL2, (par >> 5) & 1u);             // L2(c) done -> its buffer reusable
             tc::fence_after_sync();
 #endif
-            tc_issue_l1(nd, tb + kColA1, tb + kColD1 + buf * 32, c + 2, B + kBarD1 + buf);
-          } else if (c + 1 == nchunk) {
-            tc::mma_commit(B + kBarDone);
+            tc_issue_l1(na, lbo1, tb + kColA1, tb + kColD1 + buf * kTcChunk, c + kTcBufs, bars + 8 * (kBarD1 + buf));
+          } else if (c + 1 == nst) {
+            mma_commit_u32(bars + 8 * kBarDone);
           }
         }
 #if PSVO_TC_WAR_WAIT
-        if (c + 2 < nchunk) par ^= 8u;
+        if (more) par ^= 32u;
 #endif
         TC_TRACE(13);
         __syncwarp();
       }
     }
+  }
+}
+
+// MMA-issuing warp of group `grp`: every tile of the group, networks first_net..1
+template <int NPG>
+__device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, const TcPropSmem& L, int H, int grp, int work, int nst, int first_net) {
+  const uint32_t bars = tc_opaque(sm_base + L.bars + 8u * kTcBars * grp);
+  const uint32_t tb = tc_opaque(tmem + grp * 128);
+  const uint32_t lbo1 = tc_opaque((uint32_t)H * 16u);
+  TcNetAddr aq, ag;
+  aq.w1h = tc_opaque(sm_base + L.w1q_hi); aq.w1l = tc_opaque(sm_base + L.w1q_lo); aq.w1b = tc_opaque(sm_base + L.w1q_b);
+  aq.w2h = tc_opaque(sm_base + L.w2q_hi); aq.w2l = tc_opaque(sm_base + L.w2q_lo);
+  ag.w1h = tc_opaque(sm_base + L.w1g_hi); ag.w1l = tc_opaque(sm_base + L.w1g_lo); ag.w1b = tc_opaque(sm_base + L.w1g_b);
+  ag.w2h = tc_opaque(sm_base + L.w2g_hi); ag.w2l = tc_opaque(sm_base + L.w2g_lo);
+  uint32_t par = 0;
+  for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+    if (first_net == 0) tc_mma_net<16>(aq, lbo1, tb, bars, nst, par);
+    tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
   }
 }
 
@@ -269,20 +347,25 @@ __global__ void __launch_bounds__(512) tc_stage_image_kernel(PropArgs a, unsigne
 }
 
 // ---- common prologue of the three kernels that run the pipeline -------------------------------------------------------
-struct TcCtx { uint32_t tmem; uint64_t* bars; TcNetDesc nq, ng; };
+struct TcCtx { uint32_t tmem; uint64_t* bars; };
 
 // part 1 (before the kernel's own constant staging): weight image -> shared memory (one coalesced copy of what
 // tc_stage_image_kernel prepared once per pass), mbarrier init, TMEM allocation
 __device__ __forceinline__ void tc_setup_begin(unsigned char* sm, const TcPropSmem& L, const unsigned char* __restrict__ image, int tid, int warp) {
-  const uint4* src = reinterpret_cast<const uint4*>(image);
-  uint4* dst = reinterpret_cast<uint4*>(sm);
-  const int n16 = (int)(L.consts / 16);
-#pragma unroll 4
-  for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-  if (tid < kTcBars * kTcGroups) {
+  if (tid == 0) {                                                          // one thread streams the image with bulk copies (no
+    uint64_t* ib = bars + kBarImage;                                       // per-thread load/store instructions), counted on an mbarrier
+    tc::mbar_init(ib, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tc::mbar_arrive_expect_tx(ib, L.consts);
+    for (uint32_t off = 0; off < L.consts; off += 32768u) {
+      const uint32_t n = L.consts - off < 32768u ? L.consts - off : 32768u;
+      tc::bulk_g2s(sm + off, image + off, n, ib);
+    }
+  }
+  if (tid < kTcBars * kTcGroups && tid != kBarImage) {
     const int k = tid % kTcBars;
-    tc::mbar_init(bars + tid, (k == kBarA1 || k == kBarFull || k == kBarFull + 1) ? 128 : 1);
+    tc::mbar_init(bars + tid, (k == kBarA1 || (k >= kBarFull && k < kBarFull + kTcBufs)) ? 128 : 1);
   }
   if (warp == 0) tc::tmem_alloc(reinterpret_cast<uint32_t*>(sm + L.slot), 512);
 }
@@ -295,22 +378,14 @@ __device__ __forceinline__ void tc_setup_finish(unsigned char* sm, const TcPropS
   tc::fence_after_sync();
   cx.tmem = *reinterpret_cast<uint32_t*>(sm + L.slot);
   cx.bars = reinterpret_cast<uint64_t*>(sm + L.bars);
-  TcNetDesc& nq = cx.nq; TcNetDesc& ng = cx.ng;
-  nq.w1h = tc::make_desc(tc::smem_u32(sm + L.w1q_hi), H * 16, 128); nq.w1l = tc::make_desc(tc::smem_u32(sm + L.w1q_lo), H * 16, 128);
-  nq.w1b = tc::make_desc(tc::smem_u32(sm + L.w1q_b), H * 16, 128);
-  nq.w2h = tc::make_desc(tc::smem_u32(sm + L.w2q_hi), 16 * 16, 128); nq.w2l = tc::make_desc(tc::smem_u32(sm + L.w2q_lo), 16 * 16, 128);
-  nq.idesc2 = tc::make_idesc_f16(128, 16); nq.NP = 16;
-  ng.w1h = tc::make_desc(tc::smem_u32(sm + L.w1g_hi), H * 16, 128); ng.w1l = tc::make_desc(tc::smem_u32(sm + L.w1g_lo), H * 16, 128);
-  ng.w1b = tc::make_desc(tc::smem_u32(sm + L.w1g_b), H * 16, 128);
-  ng.w2h = tc::make_desc(tc::smem_u32(sm + L.w2g_hi), NPG * 16, 128); ng.w2l = tc::make_desc(tc::smem_u32(sm + L.w2g_lo), NPG * 16, 128);
-  ng.idesc2 = tc::make_idesc_f16(128, NPG); ng.NP = NPG;
+  tc::mbar_wait(cx.bars + kBarImage, 0);                                   // the weight image has landed
 }
 // a compute thread's view of its group; also writes the thread's row of the bias MMA's "ones" operand (published by the
 // thread's first arrival on the A1 barrier)
 __device__ __forceinline__ void tc_group_init(TcGroup& g, const TcCtx& cx, int grp, int warp) {
-  g.bar = cx.bars + kTcBars * grp;
+  g.bar = tc_opaque(tc::smem_u32(cx.bars + kTcBars * grp));
   g.par = 0;
-  g.tb = cx.tmem + grp * 128 + ((uint32_t)((warp & 3) * 32) << 16);
+  g.tb = tc_opaque(cx.tmem + grp * 128 + ((uint32_t)((warp & 3) * 32) << 16));
   const uint32_t ones[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};     // half2(1, 1): k = 0 multiplies b_hi, k = 1 b_lo
   tc::tmem_st8(g.tb + kColOnes, ones);
   tc::tmem_st_wait();
@@ -354,8 +429,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const int work = a.B * tiles_per_seq;
 
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, t0 ? 1 : 0, tcx.nq, tcx.ng);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");                // 128 x (96 - 32) registers released = exactly the 512 x (112 - 96) the compute warps take
+    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, t0 ? 1 : 0);
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
     const float* s1 = C; const float* sp = C + 16; const float* inv1 = C + 32; const float* inv2 = C + 48;
@@ -576,7 +653,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   const int work = a.B * tiles_per_seq;
 
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, last ? 1 : 0, tcx.nq, tcx.ng);
+    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, last ? 1 : 0);
   } else {
     const int grp = warp >> 2;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
@@ -721,7 +798,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
   const int work = (int)((rows + 127) / 128);
 
   if (warp >= kTcGroups * 4) {
-    tc_mma_warp(tcx.tmem, tcx.bars, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1, tcx.nq, tcx.ng);
+    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1);
   } else {
     const int grp = warp >> 2;
     TcGroup g;
