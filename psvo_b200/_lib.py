@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpsvo_b200.so")
+# PSVO_LIB_PATH: development hook to load an experimental build of the same library (A/B kernel variants in one GPU session)
+LIB_PATH = os.environ.get("PSVO_LIB_PATH") or os.path.join(_HERE, "lib", "libpsvo_b200.so")
 
 MAX_HIDDEN = 4
 F_BOOTSTRAP, F_TWO_Q, F_RESAMPLE, F_POISSON, F_WITH_RESAMPLING, F_SYSTEMATIC = 1, 2, 4, 8, 16, 32

@@ -15,12 +15,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(ROOT, "build", "obj")
-LIB = os.path.join(HERE, "lib", "libpsvo_b200.so")
+# PSVO_BUILD_VARIANT=name + PSVO_BUILD_DEFS="-DX=1 ...": experimental build into lib/libpsvo_b200_<name>.so (own object cache),
+# loaded with PSVO_LIB_PATH; the default build takes neither
+VARIANT = os.environ.get("PSVO_BUILD_VARIANT", "")
+OBJ = os.path.join(ROOT, "build", "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "lib", "libpsvo_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-              "-Xptxas", "-v"] + (["-DPSVO_TC_TRACE"] if os.environ.get("PSVO_TC_TRACE") == "1" else [])
+              "-Xptxas", "-v"] + (["-DPSVO_TC_TRACE"] if os.environ.get("PSVO_TC_TRACE") == "1" else []) + os.environ.get("PSVO_BUILD_DEFS", "").split()
 
 
 def _nvcc():

@@ -653,8 +653,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   const int work = a.B * tiles_per_seq;
 
   if (warp >= kTcGroups * 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
     tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, last ? 1 : 0);
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     const int grp = warp >> 2;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
     const float* inv_sg = C + 64;
@@ -798,8 +800,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
   const int work = (int)((rows + 127) / 128);
 
   if (warp >= kTcGroups * 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
     tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1);
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     const int grp = warp >> 2;
     TcGroup g;
     const int gt = tid & 127;
