@@ -907,8 +907,11 @@ bool tc_propagate_supported(const PropArgs& a) {
   const int H = a.g.width[0];
   if (a.q1.width[0] != H || H < 32 || H > 256 || (H % 32) != 0) return false;
   if (a.Dx > 16 || a.Dy > 32) return false;
-  // the tensor path pays off once the hidden layer dominates and the machine can be filled
-  if (H < 128 || (long long)a.B * a.N < 128LL * kTcGroups * 32) return false;
+  // the tensor path pays off once the hidden layer dominates and the machine can be filled (PSVO_TC_MIN_ROWS: test hook that
+  // lowers the row threshold so small reference-generated vectors can be run through the tensor-core kernels)
+  long long min_rows = 128LL * kTcGroups * 32;
+  if (const char* e = getenv("PSVO_TC_MIN_ROWS")) min_rows = atoll(e);
+  if (H < 128 || (long long)a.B * a.N < min_rows) return false;
   return true;
 }
 

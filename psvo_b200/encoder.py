@@ -17,6 +17,27 @@ def _lstm(d_in, d_h):
     return m
 
 
+def load_tf_lstm_cell(lstm, kernel, bias, forget_bias=1.0):
+    """Copy a tf.contrib.rnn.LSTMBlockCell into a one-layer torch.nn.LSTM.
+    TF: kernel [d_in + units, 4 units] applied to concat(x, h), gate order (i, c~, f, o), forget_bias added to f at run time.
+    torch: weight_ih [4 units, d_in], weight_hh [4 units, units], gate order (i, f, g = c~, o), biases b_ih + b_hh."""
+    kernel = torch.as_tensor(kernel)
+    bias = torch.as_tensor(bias)
+    u = lstm.hidden_size
+    d_in = kernel.shape[0] - u
+    assert d_in == lstm.input_size and kernel.shape[1] == 4 * u and bias.shape[0] == 4 * u
+    i, c, f, o = torch.chunk(kernel, 4, dim=1)
+    bi, bc, bf, bo = torch.chunk(bias, 4, dim=0)
+    W = torch.cat([i, f, c, o], 1)                       # torch order
+    b = torch.cat([bi, bf + forget_bias, bc, bo], 0)
+    with torch.no_grad():
+        lstm.weight_ih_l0.copy_(W[:d_in].t().to(lstm.weight_ih_l0.dtype))
+        lstm.weight_hh_l0.copy_(W[d_in:].t().to(lstm.weight_hh_l0.dtype))
+        lstm.bias_ih_l0.copy_(b.to(lstm.bias_ih_l0.dtype))
+        lstm.bias_hh_l0.zero_()
+    return lstm
+
+
 class BiRNN(torch.nn.Module):
     def __init__(self, d_in, Dhs, stack=True):
         super().__init__()
@@ -28,6 +49,15 @@ class BiRNN(torch.nn.Module):
             self.bw.append(_lstm(d, h))
             d = 2 * h if stack else h
         self.out_width = 2 * self.Dhs[-1]
+
+    def load_tf_cells(self, cells_fw, cells_bw, forget_bias=1.0):
+        """cells_*: per layer (kernel, bias) of the reference's LSTMBlockCells (src/model.py:164-179)."""
+        assert len(cells_fw) == len(self.fw) and len(cells_bw) == len(self.bw)
+        for m, (k, b) in zip(self.fw, cells_fw):
+            load_tf_lstm_cell(m, k, b, forget_bias)
+        for m, (k, b) in zip(self.bw, cells_bw):
+            load_tf_lstm_cell(m, k, b, forget_bias)
+        return self
 
     def forward(self, obs):
         """obs (B,T,D) -> (outputs_fw, outputs_bw) each (B,T,.) as the reference's `outputs` unpacks

@@ -18,6 +18,8 @@ DEFAULTS = dict(
     PSVO=True, PSVOwR=False, SVO=False, AESMC=False, IWAE=False,
     n_particles_for_BSim_proposal=16, BSim_use_single_RNN=False,
     MSE_steps=30,
+    # EXTRA (no reference counterpart, off by default): systematic instead of multinomial resampling in the forward filter
+    systematic_resampling=False,
     # trainer (runner_flag.py:118-153)
     early_stop_patience=200, lr_reduce_patience=30, lr_reduce_factor=0.7071067811865475, min_lr=3e-4, print_freq=1,
     save_model=False,

@@ -241,7 +241,7 @@ class _Rng:
         self.gen = None if seed is None else torch.Generator().manual_seed(seed)
         self.normals = None if normals is None else list(normals)
         self.uniforms = None if uniforms is None else list(uniforms)
-        self.normal_log, self.uniform_log = [], []
+        self.normal_log, self.uniform_log, self.index_log = [], [], []
 
     def normal(self, shape):
         if self.normals is not None:

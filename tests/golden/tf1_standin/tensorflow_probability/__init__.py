@@ -72,6 +72,7 @@ class Categorical:
         u = np.moveaxis(u, 0, -1)                             # (batch..., n)
         idx = resample_idx(self.logits.detach().to(torch.float32).numpy(), u)   # (batch..., n)
         idx = np.moveaxis(idx, -1, 0).reshape(ss + batch)
+        tf._rng.index_log.append(torch.from_numpy(np.ascontiguousarray(idx)).long())     # recorded for the golden vectors
         return tf.T(torch.from_numpy(np.ascontiguousarray(idx)).long())
 
 

@@ -28,8 +28,18 @@ def _dist(z, key, dtype):
     return O.Dist(O.Net(W, b), sc, smin)
 
 
+def is_big(z):
+    """BASELINE-shaped cases are stored as float32 (make_golden.py run_case(big=True)): compare at 1e-6, not 1e-11"""
+    return z["Xs"].dtype == np.float32
+
+
 def load_case(name, dtype=torch.float64):
     z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    if "X_anc" not in z and "anc" in z:                   # big cases store the drawn ancestors instead of the gathered copy
+        Xs, anc = torch.from_numpy(z["Xs"]), torch.from_numpy(z["anc"]).long()
+        z["X_anc"] = torch.gather(Xs, 2, anc[..., None].expand(*Xs.shape)).numpy()
+    if "log_Xs" not in z:                                 # log["Xs"]: X_ancestors (SVO.py:51-56) / bw_Xs (PSVO.py:43)
+        z["log_Xs"] = z["bw_Xs"] if "bw_Xs" in z and str(z["cls"]) == "PSVO" else z["X_anc"]
     F = O.Flags(use_bootstrap=bool(z["use_bootstrap"]), use_2_q=bool(z["use_2_q"]),
                 resample_particles=bool(z["resample_particles"]), poisson_emission=bool(z["poisson_emission"]))
     P = O.Params(q0=_dist(z, "q0", dtype), q1=_dist(z, "q1", dtype), g=_dist(z, "g", dtype),

@@ -10,23 +10,26 @@ import scipy.stats
 import torch
 
 from oracle import psvo_oracle as O
-from golden_io import case_names, load_case
+from golden_io import case_names, load_case, is_big
 
 FWD_CASES = case_names()
-BS_CASES = [c for c in FWD_CASES if c.startswith("psvo")]
+BS_CASES = [c for c in FWD_CASES if "psvo" in c]
 
 
 @pytest.mark.parametrize("name", FWD_CASES)
 def test_forward_filter_matches_reference_vectors(name):
     z, P, F, d = load_case(name)
+    tol = 1e-6 if is_big(z) else 1e-11                    # BASELINE-shaped vectors are stored as float32
     r = O.smc_forward(P, F, d["obs"], d["pre_obs"], d["pre_x0"], d["eps"], d["u"])
-    np.testing.assert_allclose(r["Xs"].numpy(), z["Xs"], rtol=1e-11, atol=1e-11)
-    np.testing.assert_allclose(r["log_Ws"].numpy(), z["log_Ws"], rtol=1e-11, atol=1e-11)
-    np.testing.assert_allclose(r["X_anc"].numpy(), z["X_anc"], rtol=1e-11, atol=1e-11)   # => identical ancestors
+    if "anc" in z and F.resample_particles:               # the ancestors the reference drew, index for index (free running)
+        assert np.array_equal(r["anc"].numpy(), z["anc"]), "%d ancestor mismatches" % int((r["anc"].numpy() != z["anc"]).sum())
+    np.testing.assert_allclose(r["Xs"].numpy(), z["Xs"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(r["log_Ws"].numpy(), z["log_Ws"], rtol=tol, atol=tol * 100 if is_big(z) else tol)
+    np.testing.assert_allclose(r["X_anc"].numpy(), z["X_anc"], rtol=tol, atol=tol)   # => identical ancestors
     if str(z["cls"]) in ("SVO", "AESMC", "IWAE"):
-        assert abs(float(r["log_ZSMC"]) - float(z["log_ZSMC"])) < 1e-10
+        assert abs(float(r["log_ZSMC"]) - float(z["log_ZSMC"])) < (1e-8 * abs(float(z["log_ZSMC"])) if is_big(z) else 1e-10)
         # log["Xs"] of SVO.get_log_ZSMC is X_ancestors as (B,T,N,Dx)  (src/SMC/SVO.py:51-56)
-        np.testing.assert_allclose(r["X_anc"].numpy(), z["log_Xs"], rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(r["X_anc"].numpy(), z["log_Xs"], rtol=tol, atol=tol)
 
 
 @pytest.mark.parametrize("name", BS_CASES)
@@ -36,6 +39,12 @@ def test_backward_simulation_matches_reference_vectors(name):
     wr = str(z["cls"]) == "PSVOwR"
     r = O.backward_simulation(P, F, d["obs"], d["bs_feat"], d["pre_x0"], fw["Xs"], fw["log_Ws"],
                               d["eps_bw"], d["u_bw"], with_resampling=wr, u_bw2=d["u_bw2"])
+    if is_big(z):
+        np.testing.assert_allclose(r["bw_Xs"].numpy(), z["bw_Xs"], rtol=1e-6, atol=1e-6)
+        for k in ("f_lp", "g_lp", "Omega"):
+            np.testing.assert_allclose(r[k].numpy(), z[k], rtol=1e-6, atol=1e-5)
+        assert abs(float(r["log_ZSMC"]) - float(z["log_ZSMC"])) < 1e-8 * abs(float(z["log_ZSMC"]))
+        return
     np.testing.assert_allclose(r["bw_Xs"].numpy(), z["bw_Xs"], rtol=1e-10, atol=1e-10)
     if wr:
         np.testing.assert_allclose(r["bw_log_W"].numpy(), z["bw_log_W"], rtol=1e-10, atol=1e-10)
