@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
         for (int k = 0; k < M; ++k) total += fixed_weight(cand[k * 5] - lse_m, mxn);
         uint32_t u24;
         if (a.u_pick != nullptr) u24 = u24_from_float(a.u_pick[bt * N + i]);
-        else u24 = philox4x32_10(a.seed, ((uint64_t)(a.seq_offset + b) * T + t) * N + i, 0u, 3u).v[0] >> 8;
+        else u24 = uniform_bits(a.seed, ((uint64_t)(a.seq_offset + b) * T + t) * N + i, 3u) >> 8;
         const unsigned long long thr = draw_threshold(total, u24);
         unsigned long long run = 0ull;
         sel = 0;

@@ -100,7 +100,7 @@ __global__ void fill_normal_kernel(unsigned long long seed, unsigned stream_id, 
 __global__ void fill_uniform_kernel(unsigned long long seed, unsigned stream_id, long long first, long long particles,
                                     float* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < particles; i += (long long)gridDim.x * blockDim.x)
-    out[i] = uniform_from_bits(philox4x32_10(seed, (uint64_t)(first + i), 0u, stream_id).v[0]);
+    out[i] = uniform_from_bits(uniform_bits(seed, (uint64_t)(first + i), stream_id));
 }
 
 static int grid_for(long long n, int block) {

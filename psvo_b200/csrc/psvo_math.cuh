@@ -109,6 +109,12 @@ PSVO_HD Philox4 philox4x32_10(uint64_t seed, uint64_t index, uint32_t chunk, uin
   return o;
 }
 
+// The uniform of element `index` of stream `stream_id`: word (index & 3) of the Philox block of counter index >> 2, so four
+// consecutive elements cost ONE block (the resampling kernel draws the uniforms of four consecutive children at once).
+PSVO_HD uint32_t uniform_bits(uint64_t seed, uint64_t index, uint32_t stream_id) {
+  return philox4x32_10(seed, index >> 2, 0u, stream_id).v[index & 3u];
+}
+
 // 24-bit uniform in [0,1)
 PSVO_HD float uniform_from_bits(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 

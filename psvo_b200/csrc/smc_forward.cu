@@ -443,29 +443,34 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
     if (goff != 0) for (int i = g_lo + lane; i < g_hi; i += 32) sG[i] += goff;
     __syncthreads();
   }
-  // four children per thread at a time: their branch-free binary searches interleave, hiding the shared-memory latency
-  for (int n0 = n_lo + tid; n0 < n_hi; n0 += 4 * nt) {
+  // four CONSECUTIVE children per thread at a time: their uniforms are the four words of one Philox block (uniform_bits), and
+  // their branch-free binary searches interleave, hiding the shared-memory latency
+  const bool systematic = a.flags & PSVO_F_SYSTEMATIC;
+  const uint64_t gbase = ((uint64_t)(a.seq_offset + b) * a.T + t) * N;
+  for (int n0 = n_lo + 4 * tid; n0 < n_hi; n0 += 4 * nt) {
     unsigned long long thr[4];
     int anc[4];
     bool search[4];
     int kb[4] = {0, 0, 0, 0};
+    const bool draw = resample && a.forced_anc == nullptr && a.u == nullptr;
+    const bool block4 = draw && !systematic && ((gbase + (uint64_t)n0) & 3ull) == 0ull;
+    Philox4 blk;
+    blk.v[0] = blk.v[1] = blk.v[2] = blk.v[3] = 0u;
+    if (block4) blk = philox4x32_10(a.seed, (gbase + (uint64_t)n0) >> 2, 0u, a.stream_id);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int n = n0 + k * nt;
+      const int n = n0 + k;
       anc[k] = n; search[k] = false; thr[k] = 0ull;
       if (n < n_hi && resample) {
         if (a.forced_anc != nullptr) {
           const int f = a.forced_anc[bt * N + n];
           anc[k] = f < 0 ? 0 : (f >= N ? N - 1 : f);
         } else {
-          const bool systematic = a.flags & PSVO_F_SYSTEMATIC;
           const int nu = systematic ? 0 : n;                          // systematic: one draw per (b, t), particle 0's
           uint32_t u24;
           if (a.u != nullptr) u24 = u24_from_float(a.u[bt * N + nu]);
-          else {
-            const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + nu;
-            u24 = philox4x32_10(a.seed, gidx, 0u, a.stream_id).v[0] >> 8;
-          }
+          else if (block4) u24 = blk.v[k] >> 8;
+          else u24 = uniform_bits(a.seed, gbase + (uint64_t)nu, a.stream_id) >> 8;
           if (systematic) u24 = (uint32_t)((((uint64_t)n << 24) + u24) / (uint64_t)N);   // floor(2^24 (n + u_0) / N)
           thr[k] = draw_threshold(total, u24);
           search[k] = true;
@@ -502,7 +507,7 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int n = n0 + k * nt;
+      const int n = n0 + k;
       if (n >= n_hi) continue;
       if (search[k]) anc[k] = pos[k] < N ? pos[k] : N - 1;
       if (!resample) a.logWbar[(size_t)b * N + n] = sLW[n] - lse;      // SVO.py:102,156 (IWAE keeps it differentiable)
