@@ -27,11 +27,18 @@ class PSVO(SVO):
         self.BSim_q2 = model.BSim_q2_dist
 
     def get_log_ZSMC(self, obs, hidden=None, eps=None, uniforms=None, forced_ancestors=None, seed=None,
-                     eps_bw=None, uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None):
-        logZ_b, log = self._filter_objective(obs, eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors, seed=seed,
-                                             eps_bw=eps_bw, uniforms_pick=uniforms_pick, uniforms_res=uniforms_res,
-                                             forced_pick=forced_pick, forced_anc2=forced_anc2, out=out)
-        return logZ_b.mean(), log                                                         # PSVO.py:65
+                     eps_bw=None, uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None,
+                     chunk=None, return_Xs=True, accumulate_grad=False):
+        """chunk / return_Xs / accumulate_grad: the batch memory plan of SVO.get_log_ZSMC"""
+        per_seq = dict(eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors, eps_bw=eps_bw, uniforms_pick=uniforms_pick,
+                       uniforms_res=uniforms_res, forced_pick=forced_pick, forced_anc2=forced_anc2)
+        if chunk is not None and 0 < int(chunk) < obs.shape[0]:
+            return self._chunked(obs, int(chunk), return_Xs, accumulate_grad, out, seed, per_seq)
+        logZ_b, log = self._filter_objective(obs, seed=seed, out=out, **per_seq)
+        if accumulate_grad:
+            (-logZ_b.mean()).backward()
+            logZ_b = logZ_b.detach()
+        return logZ_b.mean(), (log if return_Xs else {"Xs": None})                        # PSVO.py:65
 
     def _filter_objective(self, obs, eps=None, uniforms=None, forced_ancestors=None, seed=None, eps_bw=None,
                           uniforms_pick=None, uniforms_res=None, forced_pick=None, forced_anc2=None, out=None):

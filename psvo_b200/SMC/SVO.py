@@ -33,14 +33,57 @@ class SVO:
         self.seq_offset = 0            # global index of this rank's first sequence (multi-GPU sharding)
 
     # ------------------------------------------------------------------ public API
-    def get_log_ZSMC(self, obs, hidden=None, eps=None, uniforms=None, forced_ancestors=None, seed=None, out=None):
+    def get_log_ZSMC(self, obs, hidden=None, eps=None, uniforms=None, forced_ancestors=None, seed=None, out=None,
+                     chunk=None, return_Xs=True, accumulate_grad=False):
         """obs (B,T,Dy) CUDA tensor; hidden is accepted for signature parity (only q_uses_true_X reads it).
         Extra keyword arguments (parity / reproducibility): eps (B,T,N,Dx), uniforms (B,T,N),
         forced_ancestors (B,T,N), seed (Philox key; default: FLAGS.seed advanced per call).
-        Returns (log_ZSMC scalar, differentiable; {"Xs": (B,T,N,Dx)})."""
+        Memory plan for large batches (the reference keeps O(T N B Dx) TensorArrays alive, SVO.py:106-108; config 5 at
+        B = 1024 is ~570 GB of filter outputs): chunk=k streams the batch through the kernels k sequences at a time, re-using
+        one set of output buffers; return_Xs=False skips collecting log["Xs"]; accumulate_grad=True back-propagates every
+        chunk's share of -log_ZSMC at once (gradients accumulate in .grad, the returned scalar is detached) so that a training
+        step never holds more than one chunk.  Results do not depend on the chunking (Philox is keyed by the global sequence).
+        Returns (log_ZSMC scalar, differentiable unless accumulate_grad; {"Xs": (B,T,N,Dx) or None})."""
+        if chunk is not None and 0 < int(chunk) < obs.shape[0]:
+            return self._chunked(obs, int(chunk), return_Xs, accumulate_grad, out, seed,
+                                 dict(eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors))
         logZ_b, log = self._filter_objective(obs, eps=eps, uniforms=uniforms, forced_ancestors=forced_ancestors,
                                              seed=seed, out=out)
-        return logZ_b.mean(), log                                             # SVO.py:308-309
+        if accumulate_grad:
+            (-logZ_b.mean()).backward()
+            logZ_b = logZ_b.detach()
+        return logZ_b.mean(), (log if return_Xs else {"Xs": None})            # SVO.py:308-309
+
+    def _chunked(self, obs, chunk, return_Xs, accumulate_grad, out, seed, per_seq):
+        """get_log_ZSMC over slices of the batch; per_seq: keyword tensors with a leading batch axis (sliced alongside obs)."""
+        B = obs.shape[0]
+        if seed is None:
+            seed = (self.seed << 20) + self._calls
+            self._calls += 1
+        needs_graph = torch.is_grad_enabled() and not accumulate_grad and any(p.requires_grad for p in self.model.parameters())
+        bufs = out if out is not None else {}
+        base, zs, xs = self.seq_offset, [], []
+        try:
+            for i in range(0, B, chunk):
+                sl = slice(i, min(B, i + chunk))
+                self.seq_offset = base + i
+                kw = {k: (None if v is None else v[sl]) for k, v in per_seq.items()}
+                # a differentiable result keeps every chunk's tensors alive for autograd: fresh buffers then
+                reuse = None if needs_graph else bufs
+                logZ_b, log = self._filter_objective(obs[sl], seed=seed, out=reuse, **kw)
+                if reuse is not None and isinstance(getattr(self, "last", None), dict):
+                    raw = self.last.get("raw") or (self.last.get("filter") if "filter" in self.last else None)
+                    if isinstance(raw, dict):
+                        bufs.update({k: v for k, v in raw.items() if torch.is_tensor(v)})
+                if accumulate_grad:
+                    (-logZ_b.sum() / float(B)).backward()
+                    logZ_b = logZ_b.detach()
+                zs.append(logZ_b.clone())
+                if return_Xs:
+                    xs.append(log["Xs"].clone() if reuse is not None else log["Xs"])
+        finally:
+            self.seq_offset = base
+        return torch.cat(zs).mean(), {"Xs": torch.cat(xs, 0) if return_Xs else None}
 
     def _filter_objective(self, obs, eps=None, uniforms=None, forced_ancestors=None, seed=None, out=None):
         """Per-sequence objective logZ_b (B,) (log_ZSMC = its batch mean) and the log dict; the sequence-sharded

@@ -71,13 +71,27 @@ class ShardedObjective:
         log_ZSMC = sh.step(obs_local, optimizer)            # forward, backward, ONE all-reduce, optimizer.step()
     """
 
-    def __init__(self, smc, global_batch: int, group=None):
+    def __init__(self, smc, global_batch: int, group=None, sync_params: bool = True):
         self.smc, self.global_batch, self.group = smc, int(global_batch), group
         initialised = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if initialised else 0
         self.world = dist.get_world_size(group) if initialised else 1
         self.first, self.count = shard_bounds(self.global_batch, self.rank, self.world)
         smc.seq_offset = self.first
+        self._synced = False
+        if sync_params:
+            self.sync_parameters()
+
+    def sync_parameters(self):
+        """Replicas must start from identical parameters: broadcast every parameter from rank 0.  Networks whose input width
+        Keras infers at the first call (q0 / q2 / the backward-simulation proposals) only exist after one forward pass, so the
+        broadcast is repeated after the first step() if new parameters appeared."""
+        params = [p for p in self.smc.model.parameters()]
+        self._n_synced = len(params)
+        if self.world > 1:
+            for p in params:
+                dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        self._synced = True
 
     def forward(self, obs_local, **kw):
         """Returns (logZ_b_local (count,), log dict) -- differentiable."""
@@ -87,10 +101,13 @@ class ShardedObjective:
         return logZ_b, aux
 
     def step(self, obs_local, optimizer=None, **kw):
-        params = [p for p in self.smc.model.parameters()]
-        for p in params:
+        for p in self.smc.model.parameters():
             p.grad = None
         logZ_b, _ = self.forward(obs_local, **kw)
+        params = [p for p in self.smc.model.parameters()]            # after the forward: lazily built networks exist now
+        if len(params) != getattr(self, "_n_synced", len(params)):
+            raise RuntimeError("parameters were created during this step (lazily built networks): run one forward pass on every "
+                               "rank and call sync_parameters() before the first step, or the replicas start from different weights")
         local_loss(logZ_b, self.global_batch).backward()
         log_ZSMC = allreduce_objective(logZ_b, self.global_batch, params, self.group)
         if optimizer is not None:

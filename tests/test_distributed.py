@@ -97,3 +97,39 @@ def test_two_rank_gloo_equals_whole_batch():
         assert lz == pytest.approx(float(r["log_ZSMC"]), rel=1e-12)
         for g, p in zip(grads, leaves):
             assert torch.allclose(g, p.grad, rtol=1e-10, atol=1e-12)
+
+
+class _FakeObjective:
+    """stands in for an SMC facade on CPU: ShardedObjective only touches .model and .seq_offset at construction"""
+
+    def __init__(self, seed):
+        torch.manual_seed(seed)
+        self.model = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2))
+        self.seq_offset = 0
+
+
+def _sync_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from psvo_b200.distributed import ShardedObjective
+        obj = _FakeObjective(seed=100 + rank)                   # replicas start from DIFFERENT weights
+        sh = ShardedObjective(obj, 5)
+        ret[rank] = ([p.detach().clone() for p in obj.model.parameters()], obj.seq_offset, sh.count)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_objective_broadcasts_rank0_parameters():
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_sync_worker, args=(world, port, ret), nprocs=world, join=True)
+    ref = [p.detach() for p in _FakeObjective(seed=100).model.parameters()]
+    for rank in range(world):
+        params, off, count = ret[rank]
+        assert (off, count) == shard_bounds(5, rank, world)
+        for a, b in zip(params, ref):
+            assert torch.equal(a, b)
