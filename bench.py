@@ -14,9 +14,18 @@ collective; at 8 GPUs the global batch is exactly the 1024 of configs[4].
 
 One JSON line on rank 0.  `value` = device-timed throughput with inputs resident in HBM; `e2e` = the same through
 the reference-facing call AESMC.get_log_ZSMC(obs) with obs in pinned HOST memory (H2D copy + D2H of log_ZSMC inside
-the timed region).  `roofline` is for the dominant kernel (smc_propagate), `cpu_baseline` is the oracle restatement
-(PyTorch CPU, not TensorFlow -- TF 1.12 cannot be installed here) timed on this box's host cores.
-`--impl reference` times that CPU restatement alone (all host threads) on a bounded sample of the same workload."""
+the timed region).  `roofline` is for the dominant kernel (named in roofline.kernel from psvo_smc_forward_path),
+`cpu_baseline` is the oracle restatement (PyTorch CPU, not TensorFlow -- TF 1.12 cannot be installed here) timed on this
+box's host cores on ONE fixed slice of the workload (same B, T, N, thread count every time; median of 3).
+`--impl reference` times that CPU restatement alone on the same fixed slice.
+Extra keys of the default (c5_shard) line, every one through the reference-facing facade classes:
+  ffbsi      : the smoothing objective PSVO.get_log_ZSMC (forward filter + FFBSi backward simulation) on a bounded slice of the same
+               config, device-resident and end to end from host observations;
+  fwd_bwd    : AESMC.get_log_ZSMC + backward() (objective and its gradient) at the shard shape, T = 50;
+  train_step : the sequence-sharded training step (psvo_b200.distributed.ShardedObjective: forward, reverse mode and the ONE
+               all-reduce of [sum logZ_b | flat grads]) -- under torchrun this is the collective the design has, timed;
+  strong     : the full config-5 batch (global B = 1024) split over the ranks and streamed in chunks of 128 sequences
+               (get_log_ZSMC(chunk=128, return_Xs=False)) -- the strong-scaling point of the sweep."""
 import argparse
 import json
 import os
@@ -58,13 +67,15 @@ WORKLOADS = {
 
 
 def read_traffic(workload):
-    """measured DRAM bytes per launch of the dominant kernel (profiles/traffic.json, from ncu --set full), or None"""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json).
+    NOT measured in this run (ncu cannot run inside the timed program): returned with its source so the line says so."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(workload, {}).get("bytes_per_launch")
+            e = json.load(f).get(workload, {})
+        return e.get("bytes_per_launch"), e.get("source")
     except Exception:
-        return None
+        return None, None
 
 
 def read_peaks():
@@ -220,7 +231,8 @@ def run_ours(args, w, rank, world, local_rank):
             o = obs_host.to(dev, non_blocking=True)                   # H2D of the step's input
             log_ZSMC, _ = smc.get_log_ZSMC(o, None, out=bufs)
             return float(log_ZSMC.detach().cpu())                     # D2H of the step's result
-        step_e2e()
+        for _ in range(min(3, max(1, args.warmup))):
+            step_e2e()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -235,8 +247,9 @@ def run_ours(args, w, rank, world, local_rank):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
     logZ_mean = float(bufs["logZ_b"].detach().mean())
+    ctx = dict(smc=smc, bufs=bufs)
     if rank != 0:
-        return None
+        return None, ctx
 
     psteps = world * B * T * N
     peaks, peak_src = read_peaks()
@@ -261,24 +274,30 @@ def run_ours(args, w, rank, world, local_rank):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None}
     if args.T is None and args.B is None:
-        roof["traffic"] = read_traffic(args.workload)
-    roof.update({"kernel": "smc_filter_persistent_kernel" if kl[0] == 1 else "smc_propagate_kernel", "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
+        tr, tr_src = read_traffic(args.workload)
+        roof["traffic"] = tr
+        roof["traffic_source"] = None if tr is None else "static, NOT measured in this run: " + str(tr_src)
+    path = int(lib.psvo_smc_forward_path(C.byref(Fn.make_dims(N, B, T, Dx, w["Dy"], w["Dy"], w["Dy"], flags)),
+                                         C.byref(Fn.params_struct(P, []))))
+    kernel_name = {0: "smc_propagate_kernel (FP32, per step)", 1: "smc_filter_persistent_kernel (one launch per pass)",
+                   2: "smc_propagate_tc_kernel<32> (tcgen05, per step)"}.get(path, "?")
+    roof.update({"kernel": kernel_name, "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
                  "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
                  "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,
                  "kernel_share_of_step": {"smc_propagate": kms[0] / max(sum(kms), 1e-9), "smc_resample": kms[1] / max(sum(kms), 1e-9),
                                           "mlp_rows": kms[2] / max(sum(kms), 1e-9)},
                  "hbm_frac_whole_step": (bytes_ps * B * N * T / (step_ms * 1e-3) / 1e9) / peaks["hbm_gbs"]})
     H = w["H"]
-    if kl[0] > 1 and len(H) == 1 and H[0] >= 128 and H[0] % 32 == 0 and Dx <= 16 and w["Dy"] <= 32 and not w.get("poisson", False):
-        # tensor-core propagate kernel: what the tcgen05 pipe is actually busy with.  One M=128, K=16 instruction occupies the
-        # pipe for 40 / 48 cycles at N <= 32 / N = 64 whatever its FLOP (profiles/microbench, elect.sync issue), so the fp16x3
-        # MLPs of a 128-particle tile cost `cyc` pipe cycles although their algorithmic FLOP would need far fewer.
-        nblk = H[0] // 32
-        l1 = (nblk // 2) * 4 * 48 + (nblk % 2) * 4 * 40              # layer 1: 4 MMAs per 64-wide (or trailing 32-wide) chunk
-        cyc = 2 * l1 + nblk * 2 * (40 + 40) + nblk * 2 * (48 + 40)   # + layer 2 of q1 (N = 32, 16) and of g (N = 64, 32), 2 K-steps per block
+    if path == 2:
+        # tensor-core propagate kernel: what the tcgen05 pipe is actually busy with.  Every MMA of the pipeline is in TS form
+        # (A operand in tensor memory) and occupies the pipe for N/2 cycles (+ ~1; profiles/microbench/r2_pipe_bench.cu): per
+        # 16-unit stage layer 1 is 4 MMAs of N = 16, layer 2 is 3 MMAs of N = 16 (q1) or N = 32 (g).
+        nst = H[0] // 16
+        cyc = 2 * nst * 4 * 9 + nst * 3 * 9 + nst * 3 * 17
         tiles_per_sm = B * ((N + 127) // 128) / 148.0
         roof["tensor_pipe"] = {"pipe_cycles_per_tile": cyc, "occupancy": tiles_per_sm * cyc / (prop_ms_avg * 1e-3 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6),
-                               "note": "instruction-time occupancy of the tcgen05 pipe (min 40 cycles per M128 K16 MMA); frac above counts algorithmic fp32 FLOP against the dense bf16 peak"}
+                               "note": "instruction-time occupancy of the tcgen05 pipe (TS-form M128 K16 MMAs: N/2 + 1 cycles each); frac above "
+                                       "counts algorithmic fp32 FLOP against the dense bf16 peak although the 1e-5 bar needs a 3-term fp16 split"}
     line = {
         "metric": "particle-steps/sec (SMC forward filter)", "value": psteps / (step_ms * 1e-3), "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -293,69 +312,108 @@ def run_ours(args, w, rank, world, local_rank):
         line["e2e"] = {"value": psteps / (e2e_ms / args.steps * 1e-3), "unit": "particle-steps/s",
                        "h2d_bytes_per_step": obs_host.numel() * 4, "d2h_bytes_per_step": 4,
                        "ms_per_step": e2e_ms / args.steps, "call": "psvo_b200.SMC.AESMC.get_log_ZSMC(obs)"}
-    return line
+    return line, ctx
+
+
+def make_psvo(w, dev, seed=1234):
+    """SSM + PSVO facade of the workload's shape (reference constructor path: src/runner.py:70-81)"""
+    from psvo_b200.flags import default_flags
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.PSVO import PSVO
+    hs = ",".join(str(h) for h in w["H"])
+    dh = str(w.get("Dfeat", 64) // 2)
+    F = default_flags(Dx=w["Dx"], Dy=w["Dy"], n_particles=w["N"], n_particles_for_BSim_proposal=w["M"], time=w["T"],
+                      batch_size=w["B"], q0_layers=hs, q1_layers=hs, q2_layers=hs, f_layers=hs, g_layers=hs,
+                      y_smoother_Dhs=dh, X0_smoother_Dhs=dh, PSVO=True)
+    torch.manual_seed(seed)
+    model = SSM(F)
+    smc = PSVO(model, F)
+    return F, model, smc
 
 
 def run_ffbsi(args, w, rank, world, local_rank):
-    """psvo_ffbsi_forward alone (filter outputs resident).  value = pair evaluations M*N^2*B*(T-1) per second."""
+    """The smoothing objective through the reference-facing facade (PSVO.get_log_ZSMC = encoder + forward filter + FFBSi backward
+    simulation, src/SMC/PSVO.py:21-50), device-resident and end to end from host observations, plus the backward simulation
+    alone (PSVO.backward_simulation_w_proposal on resident filter outputs).  value = pair evaluations M*N^2*B*(T-1) per second of
+    the backward-simulation call; the per-kind kernel milliseconds explain what the whole objective spends where."""
     import ctypes as C
-    from psvo_b200 import _lib, functional as Fn
-    from oracle import psvo_oracle as O          # parameter construction only (he_normal init of the right shapes)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from gpu_util import to_dev, flags_of
+    from psvo_b200 import _lib
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = _lib.load()
     B, T, N, M, Dx, Dy = w["B"], w["T"], w["N"], w["M"], w["Dx"], w["Dy"]
-    F = O.Flags()
-    P = to_dev(O.make_params(1234, Dx, Dy, Dy, Dy, w["H"], F, ffbsi=True, Dfeat=w["Dfeat"]), dev)
-    obs = synth_obs(w, B, 1234, rank * B).to(dev)
-    g = torch.Generator().manual_seed(5)
-    feat = torch.randn(B, T, w["Dfeat"], generator=g).to(dev)
-    fw = Fn.smc_forward_raw(P, flags_of(F), obs, obs, obs[:, 0].contiguous(), N, seed=1, seq_offset=rank * B)
+    F, model, smc = make_psvo(w, dev)
+    smc.seq_offset = rank * B
+    obs_host = synth_obs(w, B, 1234, rank * B).pin_memory()
+    obs = obs_host.to(dev)
+    with torch.no_grad():
+        smc.get_log_ZSMC(obs, None, seed=1)                                   # lazy build of the Dense input widths
+        smc.SMC(None, obs, seed=1)
+        fw = smc.last                                                         # resident filter outputs for the stand-alone call
 
-    def step(seed):
-        return Fn.ffbsi_forward_raw(P, flags_of(F), obs, feat, obs[:, 0].contiguous(), fw["Xs"], fw["log_Ws"], fw["lse"], M,
-                                    seed=seed, seq_offset=rank * B)
-    for i in range(args.warmup):
-        r = step(i)
-    torch.cuda.synchronize()
+    def bsim(seed):
+        with torch.no_grad():
+            return smc.backward_simulation_w_proposal(fw["Xs"], fw["log_Ws"], obs, lse=fw["lse"], seed=seed)
+
+    def objective(seed, host=False):
+        with torch.no_grad():
+            o = obs_host.to(dev, non_blocking=True) if host else obs
+            z, _ = smc.get_log_ZSMC(o, None, seed=seed, return_Xs=False)
+            return float(z.cpu()) if host else z
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            r = fn(100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, r
+
+    for i in range(max(2, args.warmup)):
+        bsim(i); objective(i); objective(i, True)
     lib.psvo_profile_read(None, None)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        r = step(100 + i)
-    e1.record()
-    torch.cuda.synchronize()
+    ms_bsim, r = timed(bsim, args.steps)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
     launches = (C.c_int64 * 8)()
     lib.psvo_profile_read(None, launches)
+    ms_obj, zval = timed(objective, args.steps)
+    ms_e2e, zhost = timed(lambda sd: objective(sd, True), args.steps)
     lib.psvo_profile_enable(1)
-    step(999)
+    objective(999)
     torch.cuda.synchronize()
     kms, kl = (C.c_double * 8)(), (C.c_int64 * 8)()
     lib.psvo_profile_read(kms, kl)
     lib.psvo_profile_enable(0)
     pairs = world * M * N * N * B * (T - 1)
     peaks, peak_src = read_peaks()
-    rate = pairs / (ms * 1e-3)
+    rate = pairs / (ms_bsim * 1e-3)
     mufu_peak = 148 * 16 * 1.965e9
-    return {"metric": "pair-evaluations/sec (FFBSi backward simulation, psvo_ffbsi_forward)", "value": rate, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+    return {"metric": "pair-evaluations/sec (FFBSi backward simulation, PSVO.backward_simulation_w_proposal)", "value": rate, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(2, args.warmup), "ms_per_step": ms_bsim, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "note": w["note"], "class": "PSVO", "n_particles": N, "M": M, "T": T,
                        "batch_per_gpu": B, "Dx": Dx, "Dy": Dy, "mlp_hidden": w["H"], "rng": "in-kernel Philox4x32-10"},
             "gpu_launches": int(sum(launches)), "clocks": clocks,
+            "objective": {"call": "psvo_b200.SMC.PSVO.get_log_ZSMC(obs) (bi-LSTM encoder + forward filter + backward simulation)",
+                          "ms_per_call_resident": ms_obj, "ms_per_call_e2e_host_obs": ms_e2e,
+                          "h2d_bytes_per_step": obs_host.numel() * 4, "d2h_bytes_per_step": 4,
+                          "kernel_ms": {"smc_propagate": kms[0], "smc_resample": kms[1], "row MLPs": kms[2], "ffbsi": kms[5]},
+                          "note": "ms_per_call - sum(kernel_ms) = cuDNN bi-LSTM encoder, output allocation (fresh tensors per call) and "
+                                  "host gaps between the ~3T launches of the backward simulation; the round-1 driver/builder gap "
+                                  "(25.7 vs 18.2 ms) was this difference: wall time of the call vs the sum of its kernels"},
             "roofline": {"bound": "tensor", "achieved": 2 * Dx * rate / 1e12, "peak": peaks["bf16_tflops_sustained"],
                          "unit": "TFLOP/s", "frac": 2 * Dx * rate / 1e12 / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "kernel": "ffbsi step (pairwise predictive term)", "peak_source": peak_src,
+                         "kernel": "ffbsi_pair_tc_kernel (pairwise predictive term) + ffbsi_cand_tc_kernel + ffbsi_step_kernel", "peak_source": peak_src,
                          "mufu": {"achieved_ex2_per_s": rate, "peak_ex2_per_s": mufu_peak, "frac": rate / mufu_peak,
-                                  "note": "1 ex2 per pair; 148 SMs x 16/clk x 1.965 GHz"},
-                         "ffbsi_ms_per_pass": kms[5], "ffbsi_launches": int(kl[5])},
-            "log_ZSMC": float(r["logZ_b"].mean())}
+                                  "kernel_only_frac": (pairs / max(kms[5], 1e-9) * 1e3) / mufu_peak,
+                                  "note": "1 ex2 per pair; 148 SMs x 16/clk x 1.965 GHz; frac = whole backward-simulation call, "
+                                          "kernel_only_frac = against the sum of its kernels' durations"},
+                         "ffbsi_kernel_ms_per_pass": kms[5], "ffbsi_launches": int(kl[5])},
+            "log_ZSMC": float(zval)}
 
 
 def run_train_epoch(args, w, local_rank):
@@ -458,34 +516,109 @@ def run_fwd_bwd(args, w, local_rank):
             "log_ZSMC": float(z.detach())}
 
 
-def cpu_sample(w, budget_s=15.0, threads=None):
-    """Time the oracle restatement (PyTorch CPU fp32) on a bounded slice of the workload."""
+def run_train_step(args, w, rank, world, local_rank, T=50, steps=3):
+    """The sequence-sharded training step with its collective inside the timed region: forward filter + reverse mode on this
+    rank's shard, then ONE all-reduce of [sum logZ_b | flat parameter gradients] (psvo_b200.distributed.ShardedObjective.step,
+    replacing optimizer.minimize(-log_ZSMC), src/trainer.py:115-118).  T is shortened; B per rank is the workload's."""
+    from psvo_b200.distributed import ShardedObjective
+    from psvo_b200.model import SSM
+    from psvo_b200.SMC.AESMC import AESMC
+    dev = torch.device("cuda", local_rank)
+    wt = dict(w); wt["T"] = T
+    FLAGS = make_flags(wt)
+    torch.manual_seed(1234)
+    model = SSM(FLAGS).to(dev)
+    smc = AESMC(model, FLAGS)
+    smc._build_nets(w["Dy"], w["Dy"], dev)
+    B = w["B"]
+    sh = ShardedObjective(smc, B * world)
+    obs = synth_obs(wt, B, 1234, rank * B).to(dev)
+    for i in range(2):
+        sh.step(obs, None, seed=i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        z = sh.step(obs, None, seed=100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    nparam = sum(p.numel() for p in model.parameters())
+    return {"value": world * B * T * w["N"] / (ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms, "T": T,
+            "global_batch": B * world, "allreduce_bytes": 4 * (1 + nparam), "collective": "1 all-reduce per step (NCCL)" if world > 1 else "none (1 rank)",
+            "call": "ShardedObjective.step: AESMC objective + reverse mode + all-reduce of [sum logZ_b | grads]", "log_ZSMC": float(z)}
+
+
+def run_strong(args, w, rank, world, local_rank, smc, bufs, global_batch=1024, chunk=128, steps=2):
+    """Strong-scaling point: the FULL config-5 batch (1024 sequences) split over the ranks, each rank streaming its share through
+    the kernels `chunk` sequences at a time (get_log_ZSMC(chunk=, return_Xs=False): 570 GB of filter outputs never exist at once)."""
+    from psvo_b200.distributed import shard_bounds
+    dev = torch.device("cuda", local_rank)
+    first, count = shard_bounds(global_batch, rank, world)
+    obs = synth_obs(w, count, 1234, first).to(dev)
+    old = smc.seq_offset
+    smc.seq_offset = first
+
+    def step(seed):
+        with torch.no_grad():
+            z, _ = smc.get_log_ZSMC(obs, None, seed=seed, chunk=chunk, return_Xs=False, out=bufs)
+        return z
+    step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        z = step(100 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    smc.seq_offset = old
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"scaling": "strong", "global_batch": global_batch, "sequences_per_gpu": count, "chunk": chunk, "steps": steps, "warmup": 1,
+            "ms_per_step": ms, "value": global_batch * w["T"] * w["N"] / (ms * 1e-3), "unit": "particle-steps/s",
+            "call": "AESMC.get_log_ZSMC(obs, chunk=%d, return_Xs=False)" % chunk}
+
+
+CPU_SLICE = dict(B=8, T=128)        # the ONE slice of the workload both CPU legs time (capped by the workload's own B, T)
+
+
+def cpu_sample(w, reps=3, threads=None):
+    """Time the oracle restatement (PyTorch CPU fp32) on a FIXED slice of the workload: same B, T, N and thread count every
+    time, one warm-up pass, median of `reps` passes (the round-1 line sized the slice from a calibration pass and moved 30 %)."""
     from oracle import psvo_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     F = O.Flags(poisson_emission=bool(w.get("poisson", False)))
     P = O.make_params(1234, w["Dx"], w["Dy"], w["Dy"], w["Dy"], w["H"], F)
     N = w["N"]
-    Bs = min(w["B"], 8)
+    Bs, Ts = min(w["B"], CPU_SLICE["B"]), min(w["T"], CPU_SLICE["T"])
+    obs = synth_obs(w, Bs, 1234, 0)[:, :Ts]
+    g = torch.Generator().manual_seed(1)
+    eps = torch.randn(Bs, Ts, N, w["Dx"], generator=g)
+    u = torch.rand(Bs, Ts, N, generator=g)
 
-    def run(Ts):
-        obs = synth_obs(w, Bs, 1234, 0)[:, :Ts]
-        g = torch.Generator().manual_seed(1)
-        eps = torch.randn(Bs, Ts, N, w["Dx"], generator=g)
-        u = torch.rand(Bs, Ts, N, generator=g)
+    def run():
         t0 = time.perf_counter()
         with torch.no_grad():
             O.smc_forward(P, F, obs, obs, obs[:, 0], eps, u)
         return time.perf_counter() - t0
 
-    Ts = min(w["T"], 4)
-    dt = run(Ts)                                         # warm-up + calibration
-    rate = Bs * Ts * N / dt
-    Ts = int(max(4, min(w["T"], budget_s * rate / (Bs * N))))
-    dt = run(Ts)
+    with torch.no_grad():                                 # warm-up on a short prefix (thread pool, allocator)
+        O.smc_forward(P, F, obs[:, :4], obs[:, :4], obs[:, 0], eps[:, :4], u[:, :4])
+    dts = [run() for _ in range(max(1, reps))]
+    dt = statistics.median(dts)
     return {"value": Bs * Ts * N / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-            "sample": "oracle/psvo_oracle.py smc_forward (PyTorch CPU fp32 restatement, not TensorFlow), B=%d, T=%d, N=%d "
-                      "slice of %s, %.1f s" % (Bs, Ts, N, w["note"], dt),
+            "sample": "oracle/psvo_oracle.py smc_forward (PyTorch CPU fp32 restatement, not TensorFlow), fixed slice B=%d, T=%d, N=%d "
+                      "of %s; median of %d passes (%s s)" % (Bs, Ts, N, w["note"], len(dts), ", ".join("%.2f" % d for d in dts)),
             "published_reference": "TF 1.12 on an unnamed CPU box: ~14k particle-steps/s forward-only at N=16 "
                                    "(notebooks/PSVO.ipynb, BASELINE.md)"}
 
@@ -493,16 +626,10 @@ def cpu_sample(w, budget_s=15.0, threads=None):
 def run_reference(args, w, rank, world):
     if rank != 0:
         return None
-    vals = []
-    info = None
-    for _ in range(max(1, args.warmup > 0)):
-        cpu_sample(w, budget_s=2.0)
-    for _ in range(args.steps):
-        info = cpu_sample(w, budget_s=max(3.0, 45.0 / args.steps))
-        vals.append(info["value"])
-    v = statistics.median(vals)
-    info["value"] = v
-    Bs = min(w["B"], 8)
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(w, reps=1)
+    info = cpu_sample(w, reps=max(1, args.steps))
+    v = info["value"]
     return {"impl": "reference", "metric": "particle-steps/sec (SMC forward filter)", "value": v, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -521,6 +648,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ffbsi", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the train_step / strong / fwd_bwd legs of the c5_shard line")
     ap.add_argument("--T", type=int, default=None, help="override the number of time steps (debug)")
     ap.add_argument("--B", type=int, default=None, help="override sequences per GPU (debug)")
     args = ap.parse_args()
@@ -554,16 +682,35 @@ def main():
             if rank == 0:
                 print(json.dumps(line), flush=True)
             return
-        line = run_ours(args, w, rank, world, local_rank)
+        line, ctx = run_ours(args, w, rank, world, local_rank)
+        extras = args.workload == "c5_shard" and not args.no_extras and args.T is None and args.B is None
+        if extras:
+            # every rank takes part: these two carry the multi-GPU statements (the collective; the strong-scaling point)
+            train = run_train_step(args, w, rank, world, local_rank)
+            strong = run_strong(args, w, rank, world, local_rank, ctx["smc"], ctx["bufs"])
+            if rank == 0:
+                line["train_step"] = train
+                line["strong"] = strong
+        ctx = None
         if rank == 0:
             if world == 1 and not args.no_ffbsi and args.workload == "c5_shard":
-                # the FFBSi point of the same config (BASELINE metric: "SMC+FFBSi"), on a bounded slice
+                # the FFBSi point of the same config (BASELINE metric: "SMC+FFBSi"), on a bounded slice, through the PSVO facade
+                torch.cuda.empty_cache()
                 wf = dict(WORKLOADS["c5_ffbsi"])
-                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_ffbsi"; fa.steps = 2; fa.warmup = 1
+                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_ffbsi"; fa.steps = 3; fa.warmup = 2
                 fl = run_ffbsi(fa, wf, 0, 1, local_rank)
                 line["ffbsi"] = {"value": fl["value"], "unit": fl["unit"], "ms_per_pass": fl["ms_per_step"],
-                                 "mufu_frac": fl["roofline"]["mufu"]["frac"], "sample": wf["note"],
-                                 "call": "psvo_ffbsi_forward (tcgen05 pairwise term + tcgen05 candidate MLPs)"}
+                                 "mufu_frac": fl["roofline"]["mufu"]["frac"], "mufu_frac_kernels_only": fl["roofline"]["mufu"]["kernel_only_frac"],
+                                 "ffbsi_kernel_ms_per_pass": fl["roofline"]["ffbsi_kernel_ms_per_pass"],
+                                 "objective": fl["objective"], "sample": wf["note"],
+                                 "call": "PSVO.backward_simulation_w_proposal (tcgen05 pairwise term + tcgen05 candidate MLPs); objective: PSVO.get_log_ZSMC"}
+            if world == 1 and extras:
+                wb = dict(WORKLOADS["c5_fwd_bwd"])
+                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_fwd_bwd"; fa.steps = 2; fa.warmup = 2
+                fb = run_fwd_bwd(fa, wb, local_rank)
+                line["fwd_bwd"] = {"value": fb["value"], "unit": fb["unit"], "T": wb["T"], "forward_ms": fb["forward_ms"],
+                                   "backward_ms": fb["backward_ms"], "backward_over_forward": fb["backward_over_forward"],
+                                   "kernel_ms": fb["kernel_ms"], "call": "AESMC.get_log_ZSMC(obs) + (-log_ZSMC).backward()", "sample": wb["note"]}
             if world == 1 and not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_sample(w)
             print(json.dumps(line), flush=True)

@@ -225,6 +225,10 @@ PSVO_API int psvo_fill_uniform(uint64_t seed, int32_t stream_id, int64_t first_p
  * Kinds: 0 smc_propagate, 1 smc_resample, 2 mlp_rows (q0/q2 feature nets), 3 sigma, 4 smc_backward,
  *        5 ffbsi, 6 stand-alone operators. */
 #define PSVO_PROF_KINDS 8
+/* which kernels psvo_smc_forward would run for these dims / networks: 0 = per-step FP32 kernels (smc_propagate_kernel +
+   smc_resample_kernel), 1 = persistent whole-filter kernel (smc_filter_persistent_kernel, one launch per pass),
+   2 = per-step tcgen05 kernel (smc_propagate_tc_kernel) + smc_resample_kernel; <0 on invalid arguments */
+PSVO_API int psvo_smc_forward_path(const psvo_dims* d, const psvo_params* p);
 PSVO_API int psvo_profile_enable(int on);
 PSVO_API int psvo_profile_read(double* ms_by_kind, int64_t* launches_by_kind);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "psvo_version": (C.c_int, []),
     "psvo_last_error": (C.c_char_p, []),
     "psvo_smc_workspace_bytes": (_sz, [_dp, _pp]),
+    "psvo_smc_forward_path": (C.c_int, [_dp, _pp]),
     "psvo_smc_forward": (C.c_int, [_dp, _pp, _vp, _vp, _vp, _vp, _vp, _vp, _u64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "psvo_smc_backward_workspace_bytes": (_sz, [_dp, _pp]),

@@ -169,6 +169,20 @@ PSVO_API int psvo_profile_read(double* ms_by_kind, int64_t* launches_by_kind) {
 }
 PSVO_API const char* psvo_last_error(void) { return last_error().c_str(); }
 
+PSVO_API int psvo_smc_forward_path(const psvo_dims* d, const psvo_params* p) {
+  if (int e = check_dims(d)) return e;
+  if (int e = check_smc_params(d, p)) return e;
+  PropArgs pa;
+  const bool boot = d->flags & PSVO_F_BOOTSTRAP;
+  pa.q1 = p->q1.net; pa.f = boot ? p->q1.net : p->f.net; pa.g = p->g.net;
+  pa.N = d->N; pa.B = d->B; pa.T = d->T; pa.Dx = d->Dx; pa.Dy = d->Dy; pa.t = 0; pa.flags = d->flags;
+  pa.tc_image = nullptr;
+  const PropPlan plan = plan_propagate(pa);
+  if (tc_propagate_supported(pa)) return 2;
+  size_t psm = 0; int pblk = 0;
+  return persistent_filter_supported(pa, plan, &psm, &pblk) ? 1 : 0;
+}
+
 PSVO_API size_t psvo_smc_workspace_bytes(const psvo_dims* d, const psvo_params* p) {
   (void)p;
   if (d == nullptr) return 0;
