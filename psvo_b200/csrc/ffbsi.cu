@@ -86,6 +86,8 @@ int launch_particle_mlp_dx(const psvo_mlp& net, const float* in, long long seq_s
 
 struct FfbsiArgs {
   psvo_mlp f, g;
+  psvo_mlp q1_inv; float* mu1i_next;   // when mu1i_next != NULL the step also writes MLP q1_inv(picked x) = mu1i of step t-1, in place
+                                       // (a particle's own row is read by its candidates before the pick phase writes it)
   const float* sig;
   const float* obs; const float* Xs; const float* log_Ws; const float* lse;
   const float* mu_f; const float* mu1i; const float* m2_all; const float* mu_init_all; const float* mu0i;
@@ -118,6 +120,9 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
   const bool ext = a.F_ext != nullptr;        // candidate densities precomputed on tensor cores: no networks staged here
   if (!last && !ext) p = mlp_stage<DXP, DXP>(a.f, p, fs);
   if (!ext) p = mlp_stage<DXP, DYP>(a.g, p, gs);
+  MlpS<DXP, DXP> qis;
+  const bool fuse_q1i = a.mu1i_next != nullptr && !first;
+  if (fuse_q1i) p = mlp_stage<DXP, DXP>(a.q1_inv, p, qis);
   float* sMu = p; p += kPairChunk * DXP;      // mu_f[j] / s_f
   float* sWb = p; p += kPairChunk;            // normalised log weight of j
   float* sCand = p; p += blockDim.x * 5;      // omega | f | g | q | P per candidate
@@ -298,6 +303,13 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
       const float* xsel = sX + ((size_t)il * M + sel) * DXP;
       for (int d = 0; d < Dx; ++d) a.bw_Xs[(bt * N + i) * Dx + d] = xsel[d];
       a.pick[bt * N + i] = sel;
+      if (fuse_q1i) {                                                             // mu1i of step t-1 = MLP q1_inv(bw_X_t) (PSVO.py:120)
+        float xin[1][DXP], mo[1][DXP];
+#pragma unroll
+        for (int d = 0; d < DXP; ++d) xin[0][d] = d < Dx ? xsel[d] : 0.0f;
+        mlp_eval<DXP, DXP, 1>(qis, xin, mo, nullptr, 0);
+        for (int d = 0; d < Dx; ++d) a.mu1i_next[((size_t)b * N + i) * Dx + d] = mo[0][d];
+      }
       if (!wr) {
         a.out_g[bt * N + i] = gl;
         a.out_a[bt * N + i] = (om + ql) + logM;                                   // Omega
@@ -364,13 +376,16 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG; unsigned char *bimg, *tc_image; size_t bytes; };
+struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG; unsigned char *bimg, *tc_image; size_t bytes; };
 static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
   const size_t BT = (size_t)d->B * d->T, BN = (size_t)d->B * d->N;
   w.sig = take(SIG_SLOTS * 32);
   w.mu_f = take(BN * d->Dx); w.mu1i = take(BN * d->Dx);
+  // single-sequence batches (the reference's own operating point, batch_size = 1) are launch-latency bound: the transition means
+  // of ALL time steps (MLP f on the filter's particles, known up front) are then computed by one launch instead of T
+  w.mu_f_all = (d->B == 1 && (size_t)d->T * d->N * d->Dx <= (size_t)1 << 26) ? take((size_t)d->T * d->N * d->Dx) : nullptr;
   w.m2_all = take(BT * d->Dx); w.mu_init_all = take(BT * d->Dx); w.mu0i = take((size_t)d->B * d->Dx);
   w.omega_pick = take(BT * d->N);
   w.candP = nullptr; w.bimg = nullptr;
@@ -446,6 +461,7 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   a.bw_Xs = bw_Xs; a.pick = pick; a.out_f = f_lp; a.out_g = g_lp; a.out_a = Omega_or_bw_log_W;
   a.omega_pick = w.omega_pick; a.omega_all = omega_all; a.seed = seed;
   a.P_ext = nullptr;
+  a.q1_inv = p->q1_inv.net; a.mu1i_next = nullptr;
   const bool pair_tc = w.candP != nullptr;
   PairTcArgs pt;
   pt.sig = w.sig; pt.mu_f = w.mu_f; pt.mu1i = w.mu1i; pt.m2_all = w.m2_all; pt.mu_init_all = w.mu_init_all;
@@ -473,8 +489,13 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   if (IL > N) IL = N;
   int block = ((IL * M + 31) / 32) * 32;
   a.IL = IL;
+  // PSVO on the FP32 step kernel: MLP q1_inv of the picked particle (the next step's proposal mean) is evaluated by the step
+  // kernel itself instead of a launch of its own per time step
+  const bool fuse_q1i = !wr && !cand_tc;
+  if (fuse_q1i) a.mu1i_next = w.mu1i;
   const size_t smem = (5 * DXP + 32 + 4 + kPairChunk * DXP + kPairChunk + (size_t)block * 5 + (size_t)block * DXP) * sizeof(float) +
-                      (cand_tc ? 0 : staged_bytes(a.f, DXP, DXP) + staged_bytes(a.g, DXP, DYP));
+                      (cand_tc ? 0 : staged_bytes(a.f, DXP, DXP) + staged_bytes(a.g, DXP, DYP)) +
+                      (fuse_q1i ? staged_bytes(a.q1_inv, DXP, DXP) : 0);
   PSVO_REQUIRE(smem <= 227 * 1024, "psvo_ffbsi_forward: networks too large for shared memory (%zu B)", smem);
   const int64_t work = (int64_t)B * ((N + IL - 1) / IL);
   const int64_t cap = (int64_t)num_sms() * (smem > 100 * 1024 ? 1 : 2);
@@ -485,17 +506,25 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   ra.lse = nullptr; ra.logZ_b = nullptr; ra.logWbar = nullptr; ra.seed = seed;
   ra.N = N; ra.B = B; ra.T = T; ra.Dx = Dx; ra.seq_offset = d->seq_offset; ra.flags = PSVO_F_RESAMPLE; ra.stream_id = 4u;
 
+  if (w.mu_f_all != nullptr) {     // B == 1: row (t, n) of Xs -> row (t, n) of mu_f_all ("sequences" = time steps)
+    const int rc0 = DXP == 4 ? launch_particle_mlp<4>(fd.net, Xs, (long long)N * Dx, T, N, Dx, w.mu_f_all, st)
+                             : (DXP == 8 ? launch_particle_mlp<8>(fd.net, Xs, (long long)N * Dx, T, N, Dx, w.mu_f_all, st)
+                                         : launch_particle_mlp<16>(fd.net, Xs, (long long)N * Dx, T, N, Dx, w.mu_f_all, st));
+    if (rc0) return rc0;
+  }
   for (int t = T - 1; t >= 0; --t) {
     a.t = t;
     int rc = 0;
-    if (t >= 1) {      // mu_f = MLP_f(Xs[t-1])
+    if (t >= 1 && w.mu_f_all != nullptr) {
+      a.mu_f = pt.mu_f = w.mu_f_all + (size_t)(t - 1) * N * Dx;
+    } else if (t >= 1) {      // mu_f = MLP_f(Xs[t-1])
       const float* in = Xs + (size_t)(t - 1) * N * Dx;
       rc = DXP == 4 ? launch_particle_mlp<4>(fd.net, in, (long long)T * N * Dx, B, N, Dx, w.mu_f, st)
                     : (DXP == 8 ? launch_particle_mlp<8>(fd.net, in, (long long)T * N * Dx, B, N, Dx, w.mu_f, st)
                                 : launch_particle_mlp<16>(fd.net, in, (long long)T * N * Dx, B, N, Dx, w.mu_f, st));
       if (rc) return rc;
     }
-    if (t <= T - 2) {  // mu1i = MLP_q1_inv(X_{t+1}^{bw})
+    if (t <= T - 2 && !fuse_q1i) {  // mu1i = MLP_q1_inv(X_{t+1}^{bw})
       const float* in = a.X_next + (size_t)(t + 1) * N * Dx;
       rc = DXP == 4 ? launch_particle_mlp<4>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)
                     : (DXP == 8 ? launch_particle_mlp<8>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)

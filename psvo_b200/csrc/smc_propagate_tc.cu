@@ -67,6 +67,9 @@ constexpr uint32_t kColD2 = 0, kColA1 = 32, kColOnes = 48, kColD1 = 64;
 // L2 of a stage complete (only in the PSVO_TC_WAR_WAIT build) | last L2 of the network complete
 enum { kBarA1 = 0, kBarD1 = 1, kBarFull = 5, kBarL2 = 9, kBarDone = 10, kBarImage = 11 /* group 0's slot: weight image landed */ };
 // 1: wait for L2(c) to complete before L1(c+4) overwrites the accumulator it read its A operand from (conservative, slower)
+#ifndef PSVO_TC_PUBLISH_FIRST
+#define PSVO_TC_PUBLISH_FIRST 1
+#endif
 #ifndef PSVO_TC_WAR_WAIT
 #define PSVO_TC_WAR_WAIT 0
 #endif
@@ -157,6 +160,13 @@ __device__ __forceinline__ void tc_stage(TcGroup& g, int c, int nst, uint32_t (&
   TC_TRACE(1);
   tc::tmem_ld16_wait(v);
   TC_TRACE(2);
+#if PSVO_TC_PUBLISH_FIRST
+  if (c > 0) {                                                             // publish stage c-1 BEFORE anything that can stall on the
+    tc::tmem_st_wait();                                                    // MMA side: a late L1(c+1) must not hold back the arrival
+    tc::fence_before_sync();                                               // that lets L1(c+3) be issued
+    mbar_arrive_u32(g.bar + 8 * (kBarFull + PB));
+  }
+#endif
   if (c + 1 < nst) {
     mbar_wait_u32(g.bar + 8 * (kBarD1 + NB), (g.par >> NB) & 1u);          // L1 of stage c+1 complete
     g.par ^= 1u << NB;
@@ -164,11 +174,13 @@ __device__ __forceinline__ void tc_stage(TcGroup& g, int c, int nst, uint32_t (&
     tc::tmem_ld16_issue(g.tb + kColD1 + NB * kTcChunk, vn);
   }
   TC_TRACE(3);
+#if !PSVO_TC_PUBLISH_FIRST
   if (c > 0) {                                                             // publish stage c-1: its tcgen05.st was issued a stage ago
     tc::tmem_st_wait();
     tc::fence_before_sync();
     mbar_arrive_u32(g.bar + 8 * (kBarFull + PB));
   }
+#endif
   uint32_t r[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j)                                              // D1 = 16 (W1^T x + b1): the bias rode in the MMA
