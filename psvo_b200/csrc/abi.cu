@@ -1,5 +1,6 @@
 // abi.cu -- extern "C" entry points of include/psvo.h for the forward filter, plus error plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 #include "smc_kernels.h"
@@ -84,6 +85,11 @@ int check_dims(const psvo_dims* d) {
   PSVO_REQUIRE(d->Dy >= 1 && d->Dy <= PSVO_MAX_DY, "Dy=%d not in [1,%d]", d->Dy, PSVO_MAX_DY);
   PSVO_REQUIRE((int64_t)d->B * d->T * d->N < (1LL << 40), "B*T*N too large");
   return 0;
+}
+
+static bool pdl_enabled() {
+  static const bool on = !(getenv("PSVO_PDL") != nullptr && getenv("PSVO_PDL")[0] == '0');
+  return on;
 }
 
 struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; unsigned char* tc_image; size_t bytes; };
@@ -238,6 +244,10 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
     pa.t = t; ra.t = t;
     pa.anc_prev = fuse_gather && t > 0 ? anc : nullptr; pa.X_anc_w = X_anc;
     ra.skip_gather = fuse_gather && t + 1 < d->T ? 1 : 0;
+    // tensor-core path: programmatic dependent launches inside the time loop (the first propagate launch follows ordinary
+    // kernels -- sigma block, feature networks, weight image -- and keeps plain stream order)
+    pa.pdl = fuse_gather && t > 0 && pdl_enabled() ? 1 : 0;
+    ra.pdl = fuse_gather && pdl_enabled() ? 1 : 0;
     if (int e = launch_propagate(pa, plan, st)) return e;
     if (int e = launch_resample(ra, st)) return e;
   }

@@ -560,6 +560,8 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a, int 
   __shared__ unsigned long long sscr[33];
   __shared__ float fscr[33];
   int* sG = guide_off > 0 ? reinterpret_cast<int*>(smraw + guide_off) : nullptr;
+  griddep_launch_dependents();               // the next propagate launch may stage its weights while this kernel runs
+  griddep_wait();                            // log_W_t / X_t of the propagate launch before this one
   resample_body<true>(a, blockIdx.x, blockIdx.y, gridDim.y, a.t, smraw, sscr, fscr, sG, kbits);
 }
 
@@ -705,7 +707,7 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
     configured = smem;
   }
   ProfScope ps_(PK_RESAMPLE, st);
-  smc_resample_kernel<<<dim3(a.B, parts), block, smem, st>>>(a, guide_off, kbits);
+  PSVO_CUDA(launch_pdl(smc_resample_kernel, dim3(a.B, parts), dim3(block), smem, st, a.pdl != 0, a, guide_off, kbits));
   PSVO_LAUNCH_CHECK();
   return 0;
 }

@@ -35,6 +35,7 @@ struct PropArgs {
   unsigned long long seed;
   int N, B, T, Dx, Dy, t, seq_offset, scratch_half;
   unsigned flags;
+  int pdl = 0;             // 1: launch with programmatic stream serialisation (the kernel's prologue overlaps the previous kernel's tail)
 };
 struct PropPlan { int block, grid, ppt, scratch_half; size_t smem; };
 PropPlan plan_propagate(const PropArgs& a);
@@ -54,6 +55,7 @@ struct ResampleArgs {
   int N, B, T, Dx, t, seq_offset;
   unsigned flags;
   unsigned stream_id;      // Philox stream of the uniforms (1 forward filter, 4 PSVOwR second resampling)
+  int pdl = 0;             // 1: programmatic dependent launch (see PropArgs::pdl)
   int skip_gather = 0;     // 1: write anc only; X_anc[t] is produced by the propagate launch of t+1 (PropArgs::anc_prev)
 };
 int launch_resample(const ResampleArgs& a, cudaStream_t st);

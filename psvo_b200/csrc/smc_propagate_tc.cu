@@ -440,11 +440,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   const int tiles_per_seq = (N + 127) / 128;
   const int work = a.B * tiles_per_seq;
 
+  // programmatic dependent launch: everything above (weight image, barriers, TMEM) ran while the previous kernel (the resampling
+  // of step t-1) was still draining; the next kernel may start its own prologue from here on, and the first read of anything the
+  // previous kernel wrote (ancestors) comes after griddep_wait()
+  griddep_launch_dependents();
   if (warp >= kTcGroups * 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");                // 128 x (96 - 32) registers released = exactly the 512 x (112 - 96) the compute warps take
     tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, t0 ? 1 : 0);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+    griddep_wait();
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
     const float* s1 = C; const float* sp = C + 16; const float* inv1 = C + 32; const float* inv2 = C + 48;
@@ -955,7 +960,7 @@ int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
     const int max_dyn = 227 * 1024;
 #endif
     if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)); cfg = true; }
-    smc_propagate_tc_kernel<32><<<grid, kTcThreads, smem, st>>>(a);
+    PSVO_CUDA(launch_pdl(smc_propagate_tc_kernel<32>, dim3(grid), dim3(kTcThreads), smem, st, a.pdl != 0, a));
   }
   PSVO_LAUNCH_CHECK();
   return 0;
