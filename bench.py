@@ -362,14 +362,16 @@ def run_ffbsi(args, w, rank, world, local_rank):
             return float(z.cpu()) if host else z
 
     def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        """median over the iterations (each bracketed by its own events): these calls are a few hundred small launches each and
+        a busy host core shows up as an outlier, not as the kernels' time"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         torch.cuda.synchronize()
-        e0.record()
-        for i in range(steps):
+        for i, (a0, a1) in enumerate(ev):
+            a0.record()
             r = fn(100 + i)
-        e1.record()
+            a1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps, r
+        return statistics.median(a0.elapsed_time(a1) for a0, a1 in ev), r
 
     for i in range(max(2, args.warmup)):
         bsim(i); objective(i); objective(i, True)
@@ -488,7 +490,7 @@ def run_fwd_bwd(args, w, local_rank):
         step(i)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    fwd_ms = bwd_ms = 0.0
+    fwd_l, bwd_l = [], []
     for i in range(args.steps):
         for p in model.parameters():
             p.grad = None
@@ -498,8 +500,8 @@ def run_fwd_bwd(args, w, local_rank):
         (-z).backward()
         ev[2].record()
         torch.cuda.synchronize()
-        fwd_ms += ev[0].elapsed_time(ev[1]); bwd_ms += ev[1].elapsed_time(ev[2])
-    fwd_ms /= args.steps; bwd_ms /= args.steps
+        fwd_l.append(ev[0].elapsed_time(ev[1])); bwd_l.append(ev[1].elapsed_time(ev[2]))
+    fwd_ms, bwd_ms = statistics.median(fwd_l), statistics.median(bwd_l)        # median: the reverse pass is ~10^3 launches, host noise shows
     lib.psvo_profile_enable(1)
     step(999)
     torch.cuda.synchronize()
@@ -516,7 +518,7 @@ def run_fwd_bwd(args, w, local_rank):
             "log_ZSMC": float(z.detach())}
 
 
-def run_train_step(args, w, rank, world, local_rank, T=50, steps=3):
+def run_train_step(args, w, rank, world, local_rank, T=50, steps=5):
     """The sequence-sharded training step with its collective inside the timed region: forward filter + reverse mode on this
     rank's shard, then ONE all-reduce of [sum logZ_b | flat parameter gradients] (psvo_b200.distributed.ShardedObjective.step,
     replacing optimizer.minimize(-log_ZSMC), src/trainer.py:115-118).  T is shortened; B per rank is the workload's."""
@@ -538,13 +540,13 @@ def run_train_step(args, w, rank, world, local_rank, T=50, steps=3):
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i, (a0, a1) in enumerate(ev):
+        a0.record()
         z = sh.step(obs, None, seed=100 + i)
-    e1.record()
+        a1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    t = torch.tensor([statistics.median(a0.elapsed_time(a1) for a0, a1 in ev)], device=dev, dtype=torch.float64)   # median: host-launch noise
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t[0])
@@ -697,7 +699,7 @@ def main():
                 # the FFBSi point of the same config (BASELINE metric: "SMC+FFBSi"), on a bounded slice, through the PSVO facade
                 torch.cuda.empty_cache()
                 wf = dict(WORKLOADS["c5_ffbsi"])
-                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_ffbsi"; fa.steps = 3; fa.warmup = 2
+                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_ffbsi"; fa.steps = 5; fa.warmup = 2
                 fl = run_ffbsi(fa, wf, 0, 1, local_rank)
                 line["ffbsi"] = {"value": fl["value"], "unit": fl["unit"], "ms_per_pass": fl["ms_per_step"],
                                  "mufu_frac": fl["roofline"]["mufu"]["frac"], "mufu_frac_kernels_only": fl["roofline"]["mufu"]["kernel_only_frac"],
@@ -706,7 +708,7 @@ def main():
                                  "call": "PSVO.backward_simulation_w_proposal (tcgen05 pairwise term + tcgen05 candidate MLPs); objective: PSVO.get_log_ZSMC"}
             if world == 1 and extras:
                 wb = dict(WORKLOADS["c5_fwd_bwd"])
-                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_fwd_bwd"; fa.steps = 2; fa.warmup = 2
+                fa = argparse.Namespace(**vars(args)); fa.workload = "c5_fwd_bwd"; fa.steps = 5; fa.warmup = 2
                 fb = run_fwd_bwd(fa, wb, local_rank)
                 line["fwd_bwd"] = {"value": fb["value"], "unit": fb["unit"], "T": wb["T"], "forward_ms": fb["forward_ms"],
                                    "backward_ms": fb["backward_ms"], "backward_over_forward": fb["backward_over_forward"],
