@@ -507,6 +507,7 @@ static size_t staged_floats(const psvo_mlp& net, int din_pad, int dout_pad) {
 struct BwdWs {
   float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp;
   float *tc_mu, *tc_muq, *tc_g; unsigned char *img_g, *img_q1, *img_fwd; unsigned int* gmax;     // tensor-core reverse mode (or NULL)
+  float *rows_x, *rows_gx;                                                                       // generic row-MLP reverse mode: deep networks (or NULL)
   size_t bytes;
 };
 static bool tc_backward_ok(const psvo_dims* d, const psvo_params* p) {
@@ -515,6 +516,13 @@ static bool tc_backward_ok(const psvo_dims* d, const psvo_params* p) {
   const long long rows = (long long)d->B * d->N;
   return mlp_bwd_tc_supported(p->q1.net, rows) && mlp_bwd_tc_supported(p->g.net, rows) &&
          tc_pipeline_supported(p->q1.net, p->g.net, d->Dx, d->Dy) && rows < (1LL << 31);
+}
+// per-particle networks with more than one hidden layer: reverse mode through the generic row-MLP kernels (any depth), with
+// this file's upstream-gradient kernels in between -- the structure of the tensor-core path, default flag combination only
+static bool deep_rows_backward(const psvo_dims* d, const psvo_params* p) {
+  if (p == nullptr) return false;
+  if (!(d->flags & PSVO_F_BOOTSTRAP) || !(d->flags & PSVO_F_TWO_Q)) return false;
+  return p->q1.net.n_hidden >= 2 || p->g.net.n_hidden >= 2;
 }
 static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
   BwdWs w;
@@ -536,8 +544,27 @@ static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
     w.img_q1 = reinterpret_cast<unsigned char*>(take(mlp_bwd_tc_image_bytes(p->q1.net) / sizeof(float) + 64));
     w.gmax = reinterpret_cast<unsigned int*>(take(64));
   }
+  w.rows_x = w.rows_gx = nullptr;
+  if (!tc_backward_ok(d, p) && deep_rows_backward(d, p)) {
+    const size_t wide = d->Dx > d->Dy ? d->Dx : d->Dy;
+    w.tc_mu = take(BN * d->Dy); w.tc_muq = take(BN * d->Dx); w.tc_g = take(BN * wide);
+    w.rows_x = take(BN * d->Dx); w.rows_gx = take(BN * d->Dx);
+  }
   w.bytes = off;
   return w;
+}
+
+// gXout[b][anc[b][n]][:] += gx[b][n][:]  (a child's gradient flows to its resampled parent, SVO.py:254-257 under autodiff)
+__global__ void scatter_parent_kernel(const float* __restrict__ gx, const int* __restrict__ anc, long long anc_seq_stride,
+                                      float* __restrict__ gXout, int B, int N, int Dx) {
+  const long long total = (long long)B * N * Dx;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / Dx;
+    const int d = (int)(e - row * Dx);
+    const int b = (int)(row / N), n = (int)(row - (long long)b * N);
+    const int parent = anc[(long long)b * anc_seq_stride + n];
+    atomicAdd(gXout + ((long long)b * N + parent) * Dx + d, gx[e]);
+  }
 }
 
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
@@ -574,8 +601,9 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   PSVO_REQUIRE(g_log_Ws == nullptr || (d->flags & PSVO_F_RESAMPLE),
                "psvo_smc_backward: an incoming g_log_Ws is only supported with resampling (PSVO / PSVOwR always resample)");
   const psvo_dist& fd = boot ? p->q1 : p->f;
-  PSVO_REQUIRE(p->q1.net.n_hidden <= 1 && p->g.net.n_hidden <= 1 && fd.net.n_hidden <= 1,
-               "psvo_smc_backward: per-particle networks (q1, f, g) with more than one hidden layer are not supported by the reverse-mode kernels yet");
+  const bool deep = p->q1.net.n_hidden >= 2 || p->g.net.n_hidden >= 2 || fd.net.n_hidden >= 2;
+  PSVO_REQUIRE(!deep || f_is_d1,
+               "psvo_smc_backward: per-particle networks (q1, f, g) with more than one hidden layer need use_bootstrap and use_2_q in reverse mode");
   const BwdWs w = carve_bwd(d, p, static_cast<char*>(ws));
   PSVO_REQUIRE(ws_bytes >= w.bytes, "workspace too small: %zu < %zu", ws_bytes, w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
@@ -632,7 +660,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   // tensor-core reverse mode (default flags, one hidden layer of 64..256 units, >= 8192 particles per step): the two
   // per-particle networks run as  tcgen05 forward (mu) -> this file's kernels without their MLP part (upstream gradient,
   // sigma statistics, per-sequence reductions) -> tcgen05 reverse (mlp_bwd_tc.cu: gx, dW, db)
-  const bool tc = w.tc_mu != nullptr;
+  const bool tc = w.img_g != nullptr;
   if (tc) {
     PSVO_CUDA(cudaMemsetAsync(w.img_g, 0, mlp_bwd_tc_image_bytes(a.g), st));
     PSVO_CUDA(cudaMemsetAsync(w.img_q1, 0, mlp_bwd_tc_image_bytes(a.q1), st));
@@ -685,6 +713,43 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
                       : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
                                   : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
         if (rc) return rc;
+      }
+      float* tmp = gXin; gXin = gXout; gXout = tmp;
+      continue;
+    }
+    if (w.rows_x != nullptr) {
+      // ---- deep networks: forward and reverse through the generic row-MLP kernels on this step's rows, staged contiguously
+      const size_t pitch = (size_t)T * N * Dx * sizeof(float), width = (size_t)N * Dx * sizeof(float);
+      PSVO_CUDA(cudaMemcpy2DAsync(w.rows_x, width, Xs + (size_t)t * N * Dx, pitch, width, B, cudaMemcpyDeviceToDevice, st));
+      if (int e = launch_mlp_rows_forward(a.g, w.rows_x, (int64_t)BN, w.tc_mu, st)) return e;
+      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g;
+      {
+        ProfScope ps_(PK_BWD, st);
+        emission_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+        PSVO_LAUNCH_CHECK();
+      }
+      if (int e = launch_mlp_rows_backward(a.g, w.rows_x, w.tc_g, (int64_t)BN, w.gXg, &a.gg, st)) return e;
+      if (t > 0) {
+        PSVO_CUDA(cudaMemcpy2DAsync(w.rows_x, width, X_anc + (size_t)(t - 1) * N * Dx, pitch, width, B, cudaMemcpyDeviceToDevice, st));
+        if (int e = launch_mlp_rows_forward(a.q1, w.rows_x, (int64_t)BN, w.tc_muq, st)) return e;
+        a.ext_mu = w.tc_muq;
+        {
+          ProfScope ps_(PK_BWD, st);
+          proposal_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+          PSVO_LAUNCH_CHECK();
+        }
+        if (int e = launch_mlp_rows_backward(a.q1, w.rows_x, w.tc_g, (int64_t)BN, w.rows_gx, &a.gq1, st)) return e;
+        {
+          ProfScope ps_(PK_BWD, st);
+          scatter_parent_kernel<<<light_grid, 256, 0, st>>>(w.rows_gx, anc + (size_t)(t - 1) * N, (long long)T * N, gXout, B, N, Dx);
+          PSVO_LAUNCH_CHECK();
+        }
+      } else {
+        a.ext_mu = nullptr; a.ext_g = nullptr;
+        const int rc0 = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP, smP), smP, st)
+                                 : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
+                                             : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
+        if (rc0) return rc0;
       }
       float* tmp = gXin; gXin = gXout; gXout = tmp;
       continue;

@@ -28,6 +28,11 @@ CASES = [
     ("tensor_core_ragged", 5, 7, 6, 9, [128], 3000, 3, 3, O.Flags()),
     ("tensor_core_poisson_h64", 4, 1, 8, 8, [64], 2100, 4, 3, O.Flags(poisson_emission=True)),
     ("tensor_core_iwae", 4, 2, 4, 4, [64], 2100, 4, 3, O.Flags(resample_particles=False)),
+    # per-particle networks deeper than one hidden layer (the reference accepts any depth, src/model.py:27-31): reverse mode
+    # through the generic row-MLP kernels
+    ("deep_mlp", 3, 2, 4, 5, [16, 12, 8], 130, 2, 4, O.Flags()),
+    ("deep_mlp_two_layers_poisson", 4, 1, 6, 6, [24, 16], 300, 3, 3, O.Flags(poisson_emission=True)),
+    ("deep_mlp_iwae", 2, 2, 3, 3, [12, 12], 64, 2, 4, O.Flags(resample_particles=False)),
 ]
 
 
