@@ -1,6 +1,10 @@
 """-m gpu parity tests of the reverse-mode kernels (psvo_smc_backward) against fp64 autograd of the oracle,
-teacher-forced on the kernel's own ancestor indices.  Tolerance: 1e-5 of the largest entry of each gradient
-tensor (north_star: gradients within 1e-5 relative, fp32), with a small slack for the fp32 atomics."""
+teacher-forced on the kernel's own ancestor indices.  Tolerance: the forward filter's gradients within 1e-5 of the largest
+entry of each gradient tensor (north_star: 1e-5 relative, fp32; measured worst 6.9e-6).  The smoothing objectives (PSVO / PSVOwR)
+keep 5e-5: their gradient runs through the pairwise term, a softmax over N x M fp32 log-densities evaluated as a fp16x3 tensor-core
+product in the forward pass and as fp32 sums over N partners in the reverse pass.  Measured worst per case (printed by the test):
+1.3e-5 (q0.W1, N=16), 2.1e-5 (bsim_q2.sigma_con, config-2 shape), 3.1e-5 (q2.W0, config-5 shape), <= 8e-6 elsewhere -- always a
+parameter whose gradient sums terms of all B*T*N particles that went through that softmax."""
 import pytest
 import torch
 
@@ -84,12 +88,12 @@ def test_gradients_vs_oracle_autograd(cfg):
         scale = max(float(r.abs().max()), 1e-3)
         err = float((g.double().cpu() - r).abs().max()) / scale
         worst = max(worst, err)
-        assert err < 3e-5, "%s: max err %.3e of max |grad| %.3e" % (key, err, scale)
+        assert err < 1e-5, "%s: max err %.3e of max |grad| %.3e" % (key, err, scale)          # north_star: 1e-5 relative (fp32)
     if F.use_2_q:
-        assert_close(pre_obs_d.grad, po.grad, 0, 3e-5 * max(float(po.grad.abs().max()), 1e-3), "g_pre_obs")
+        assert_close(pre_obs_d.grad, po.grad, 0, 1e-5 * max(float(po.grad.abs().max()), 1e-3), "g_pre_obs")
     else:
         assert float(pre_obs_d.grad.abs().max()) == 0.0
-    assert_close(pre_x0_d.grad, px.grad, 0, 3e-5 * max(float(px.grad.abs().max()), 1e-3), "g_pre_x0")
+    assert_close(pre_x0_d.grad, px.grad, 0, 1e-5 * max(float(px.grad.abs().max()), 1e-3), "g_pre_x0")
     print("%s: worst relative gradient error %.2e" % (name, worst))
 
 
@@ -198,13 +202,14 @@ def test_smoothing_gradients_vs_oracle_autograd(cfg):
             got["%s.W%d" % (nm, k)], got["%s.b%d" % (nm, k)] = w.grad, b.grad
         if dp.sigma_con is not None:
             got[nm + ".sigma_con"] = dp.sigma_con.grad
-    worst, bad = 0.0, []
+    worst, worst_key, bad = 0.0, "", []
     for key, t in smooth_leaves_of(P64):
         r = t.grad if t.grad is not None else torch.zeros_like(t)
         gg = got[key] if got[key] is not None else torch.zeros_like(t, dtype=torch.float32, device=DEV)
         scale = max(float(r.abs().max()), 1e-3)
         err = float((gg.double().cpu() - r).abs().max()) / scale
-        worst = max(worst, err)
+        if err > worst:
+            worst, worst_key = err, key
         if err >= 5e-5:
             bad.append("%s: max err %.3e of max |grad| %.3e" % (key, err, scale))
     assert not bad, "; ".join(bad)
@@ -213,7 +218,7 @@ def test_smoothing_gradients_vs_oracle_autograd(cfg):
     assert_close(pre_x0_d.grad, gx0, 0, 5e-5 * max(float(gx0.abs().max()), 1e-3), "g_pre_x0")
     if F.use_2_q:
         assert_close(pre_obs_d.grad, po.grad, 0, 5e-5 * max(float(po.grad.abs().max()), 1e-3), "g_pre_obs")
-    print("%s: worst relative gradient error %.2e" % (name, worst))
+    print("%s: worst relative gradient error %.2e (%s)" % (name, worst, worst_key))
 
 
 def test_psvo_facade_training_step_reduces_loss():
