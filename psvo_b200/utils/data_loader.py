@@ -15,7 +15,7 @@ def load_data(path, Dx, isPython2=False, q_uses_true_X=False):
     held_out = [np.asarray(data[k]) for k in ("Ytest", "Yvalid") if k in data]
     if not held_out:
         raise ValueError("obs test set is not found")
-    # with both present the reference keeps the larger one, Ytest on ties (data_loader.py:12-15)
+    # with both present the reference keeps the larger one, Yvalid on ties (data_loader.py:12-15)
     obs_test = held_out[0] if len(held_out) == 1 or held_out[0].shape[0] > held_out[1].shape[0] else held_out[1]
 
     if obs_train.ndim == 2:                                   # (n, time) recordings: Dy = 1

@@ -59,3 +59,48 @@ def test_runner_main_on_fhn_slice(tmp_path):
     assert d["learned_model_dict"]["Xs_val"].shape == (2, 200, 16, 2) and len(d["learned_model_dict"]["y_hat_val"]) == 4
     with pytest.raises(ValueError):
         runner.objective_class(runner.parse_flags(["--PSVO", "True", "--SVO", "True"]))
+
+
+REAL = [
+    # fixture, class, Dx, flags of the BASELINE config the data belongs to (reduced where noted)
+    # configs[1]: Lorenz attractor, SVO with FFBSi backward simulation = class PSVO, n_particles 256, T 500 (the surviving pickles have Dy = 1)
+    ("lorenz_slice.p", "PSVO", 3, dict(n_particles=256, n_particles_for_BSim_proposal=16)),
+    ("lorenz10d_slice.p", "PSVO", 3, dict(n_particles=64, n_particles_for_BSim_proposal=8)),
+    # configs[3]: Allen / Hodgkin-Huxley recordings, Dx = 4, "Poisson" emission, width 64, n_particles 2048, T 1000
+    ("allen_slice.p", "SVO", 4, dict(n_particles=2048, poisson_emission=True, q0_layers="64", q1_layers="64", q2_layers="64",
+                                     f_layers="64", g_layers="64")),
+    ("hh_slice.p", "SVO", 4, dict(n_particles=2048, poisson_emission=True, q0_layers="64", q1_layers="64", q2_layers="64",
+                                  f_layers="64", g_layers="64")),
+]
+
+
+@pytest.mark.parametrize("fixture,cls_name,Dx,over", REAL, ids=[r[0][:-2] for r in REAL])
+def test_train_on_real_recordings(fixture, cls_name, Dx, over, tmp_path):
+    """BASELINE configs[1] / configs[3] on slices of the reference's own Lorenz / Allen / Hodgkin-Huxley pickles at the configs'
+    particle counts and full sequence length: two epochs of the eager trainer, batch 1 (the reference's default)"""
+    from psvo_b200.flags import default_flags
+    from psvo_b200.model import SSM
+    from psvo_b200.trainer import trainer
+    from psvo_b200.utils.data_loader import load_data
+    import importlib
+    cls = getattr(importlib.import_module("psvo_b200.SMC." + cls_name), cls_name)
+    hidden_train, hidden_test, obs_train, obs_test = load_data(os.path.join(HERE, "golden", fixture), Dx=Dx)
+    if fixture.startswith(("allen", "hh")):
+        # membrane potentials in mV: the reference's runs standardise nothing, its "Poisson" emission is a unit-variance Gaussian on a
+        # softplus rate (src/distribution/poisson.py:37) -- rescaled here so the initial objective stays in fp32 range
+        s = float(np.abs(obs_train).max())
+        obs_train, obs_test = obs_train / s * 5.0, obs_test / s * 5.0
+    T, Dy = obs_train.shape[1], obs_train.shape[2]
+    torch.manual_seed(0)
+    F = default_flags(Dx=Dx, Dy=Dy, batch_size=1, epoch=2, lr=3e-3, MSE_steps=3, time=T, SVO=(cls_name == "SVO"),
+                      PSVO=(cls_name == "PSVO"), seed=5, **over)
+    model = SSM(F)
+    tr = trainer(model, cls(model, F), F)
+    tr.init_data_saving(str(tmp_path))
+    metrics, log = tr.train(obs_train, obs_test, hidden_train, hidden_test, print_freq=1)
+    lz = metrics["log_ZSMC_trains"]
+    print("real data %s (%s, N=%d, T=%d, Dy=%d): log_ZSMC train %s, valid %s" % (
+        fixture, cls_name, F.n_particles, T, Dy, ["%.1f" % v for v in lz], ["%.1f" % v for v in metrics["log_ZSMC_tests"]]))
+    assert len(lz) == 3 and all(np.isfinite(lz)) and all(np.isfinite(metrics["log_ZSMC_tests"]))
+    assert lz[-1] > lz[0]                                            # two epochs of Adam improve the training objective
+    assert log["Xs"].shape[1:] == (T, F.n_particles, Dx)

@@ -20,6 +20,25 @@ def test_load_fhn_slice_fixture():
     assert np.isfinite(obs_train).all() and float(np.abs(obs_train).max()) < 10
 
 
+def test_load_real_data_slices():
+    """fixtures cut from the reference's Lorenz / Allen / Hodgkin-Huxley pickles (tests/golden/make_real_slices.py): shapes, the
+    added Dy axis of 2-D recordings, the held-out tie rule (Yvalid), zero hidden states where the file has none"""
+    g = os.path.join(HERE, "golden")
+    ht, hv, ot, ov = load_data(os.path.join(g, "lorenz_slice.p"), Dx=3)
+    assert ot.shape == (4, 500, 1) and ov.shape == (2, 500, 1) and ht.shape == (4, 500, 3) and hv.shape == (2, 500, 3)
+    assert float(np.abs(ht).max()) > 1.0                                     # Xtrue present: real latent trajectories
+    ht, hv, ot, ov = load_data(os.path.join(g, "lorenz10d_slice.p"), Dx=3)
+    with open(os.path.join(g, "lorenz10d_slice.p"), "rb") as f:
+        import pickle
+        raw = pickle.load(f)
+    assert ot.shape == (3, 250, 10) and np.array_equal(ov, raw["Yvalid"])    # Ytest and Yvalid tie: Yvalid (data_loader.py:12-15)
+    assert float(np.abs(ht).max()) == 0.0 and hv.shape == (2, 250, 3)        # no Xtrue / Xtrain key ("State" is not read)
+    ht, hv, ot, ov = load_data(os.path.join(g, "allen_slice.p"), Dx=4)
+    assert ot.shape == (3, 1000, 1) and ov.shape == (2, 1000, 1) and ht.shape == (3, 1000, 4)
+    ht, hv, ot, ov = load_data(os.path.join(g, "hh_slice.p"), Dx=4)
+    assert ot.shape == (3, 1000, 1) and ov.shape == (2, 1000, 1)
+
+
 def test_loader_rules(tmp_path):
     """src/utils/data_loader.py:5-45: larger of Ytest/Yvalid (Ytest on ties... only if strictly larger), 2-D recordings
     get a trailing axis, missing latents become zeros unless q_uses_true_X."""
