@@ -244,10 +244,10 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
     pa.t = t; ra.t = t;
     pa.anc_prev = fuse_gather && t > 0 ? anc : nullptr; pa.X_anc_w = X_anc;
     ra.skip_gather = fuse_gather && t + 1 < d->T ? 1 : 0;
-    // tensor-core path: programmatic dependent launches inside the time loop (the first propagate launch follows ordinary
-    // kernels -- sigma block, feature networks, weight image -- and keeps plain stream order)
-    pa.pdl = fuse_gather && t > 0 && pdl_enabled() ? 1 : 0;
-    ra.pdl = fuse_gather && pdl_enabled() ? 1 : 0;
+    // programmatic dependent launches inside the time loop (the first propagate launch follows ordinary kernels -- sigma
+    // block, feature networks, weight image -- and keeps plain stream order)
+    pa.pdl = t > 0 && pdl_enabled() ? 1 : 0;
+    ra.pdl = pdl_enabled() ? 1 : 0;
     if (int e = launch_propagate(pa, plan, st)) return e;
     if (int e = launch_resample(ra, st)) return e;
   }

@@ -235,6 +235,10 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
   p = mlp_stage<DXP, DYP>(a.g, p, gs);
   float* scratch = p;
   step_consts_init<DXP>(a, t0, C);
+  // programmatic dependent launch (PropArgs::pdl): the weights and constants above were staged while the resampling launch of
+  // step t-1 was still running; its outputs (X_anc, log Wbar) are first read below
+  griddep_launch_dependents();
+  griddep_wait();
 
   const int tile = blockDim.x * PPT;
   const int tiles_per_seq = (N + tile - 1) / tile;
@@ -254,7 +258,7 @@ static int launch_propagate_t(const PropArgs& a, int block, int grid, size_t sme
     configured = smem;
   }
   ProfScope ps_(PK_PROP, st);
-  kern<<<grid, block, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, a.pdl != 0, a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }
