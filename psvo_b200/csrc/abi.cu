@@ -87,11 +87,6 @@ int check_dims(const psvo_dims* d) {
   return 0;
 }
 
-static bool pdl_enabled() {
-  static const bool on = !(getenv("PSVO_PDL") != nullptr && getenv("PSVO_PDL")[0] == '0');
-  return on;
-}
-
 struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; unsigned char* tc_image; size_t bytes; };
 
 FwdWs carve_fwd(const psvo_dims* d, void* ws) {

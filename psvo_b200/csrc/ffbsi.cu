@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) particle_mlp_kernel(psvo_mlp net, const f
   extern __shared__ __align__(16) float smem[];
   MlpS<DIN, DOUT> s;
   mlp_stage<DIN, DOUT>(net, smem, s);
+  griddep_entry();                       // weights staged while the previous kernel drained; `in` is read below
   __syncthreads();
   const long long rows = (long long)B * N;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
@@ -70,7 +71,7 @@ static int launch_particle_mlp(const psvo_mlp& net, const float* in, long long s
   long long grid = (rows + block - 1) / block;
   if (grid > 4LL * num_sms()) grid = 4LL * num_sms();
   ProfScope ps_(PK_FFBSI, st);
-  kern<<<(unsigned)grid, block, smem, st>>>(net, in, seq_stride, B, N, Dx, Dx, out);
+  PSVO_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(block), smem, st, pdl_enabled(), net, in, seq_stride, B, N, Dx, Dx, out));
   PSVO_LAUNCH_CHECK();
   return 0;
 }
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     sinit[d] = a.sig[((boot && two_q) ? SIG_Q0 : (boot ? SIG_Q1 : SIG_F)) * 32 + d];
   }
   for (int i = threadIdx.x; i < 32; i += blockDim.x) sg[i] = a.sig[SIG_G * 32 + i];
+  griddep_entry();                       // networks and sigmas (constant over the pass) staged; the previous step's outputs are read below
   __syncthreads();
   if (threadIdx.x == 0) {
     float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -371,7 +373,7 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
     configured = smem;
   }
   ProfScope ps_(PK_FFBSI, st);
-  kern<<<grid, block, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }

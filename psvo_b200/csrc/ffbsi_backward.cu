@@ -71,6 +71,7 @@ __device__ __forceinline__ void warp_acc(float v, float* dst) {
 // ------------------------------------------------------------------------------------------------------
 template <int DXP, int DYP>
 __global__ void __launch_bounds__(256) ffbsi_bwd_cand_kernel(FbArgs a) {
+  griddep_entry();
   extern __shared__ __align__(16) float smem[];
   const int Dx = a.Dx, Dy = a.Dy, N = a.N, M = a.M, T = a.T, t = a.t;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP, two_q = a.flags & PSVO_F_TWO_Q, poisson = a.flags & PSVO_F_POISSON;
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_cand_kernel(FbArgs a) {
 // ------------------------------------------------------------------------------------------------------
 template <int DXP>
 __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
+  griddep_entry();
   extern __shared__ __align__(16) float smem[];
   const int Dx = a.Dx, N = a.N, M = a.M, T = a.T, t = a.t;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP;
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
 // ------------------------------------------------------------------------------------------------------
 template <int DXP>
 __global__ void __launch_bounds__(256) ffbsi_bwd_traj_kernel(FbArgs a) {
+  griddep_entry();
   extern __shared__ __align__(16) float smem[];
   const int Dx = a.Dx, N = a.N, T = a.T, t = a.t;
   const bool wr = a.flags & PSVO_F_WITH_RESAMPLING;
@@ -622,7 +625,7 @@ static int launch_fb(K kern, const FbArgs& a, int grid, int block, size_t smem, 
     }
   }
   ProfScope ps_(PK_FFBSI, st);
-  kern<<<grid, block, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }

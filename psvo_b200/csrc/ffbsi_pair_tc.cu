@@ -41,6 +41,7 @@ constexpr float kPtSentinel = -60000.0f; // c_j of padded columns / zero-weight 
 
 // ---- B image: per (sequence, 128-column tile) the UMMA B operand [N = 128 rows j][K] ----------------------------
 __global__ void __launch_bounds__(128) ffbsi_pair_prep_kernel(PairTcArgs a) {
+  griddep_entry();
   const int b = blockIdx.y;
   const int N = a.N, Dx = a.Dx, NT = (N + kPtCols - 1) / kPtCols;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP;
@@ -117,6 +118,7 @@ __host__ __device__ inline PtSmem pt_layout() {
 
 __global__ void __launch_bounds__(kPtThreads, 1) ffbsi_pair_tc_kernel(PairTcArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
+  griddep_entry();
   const PtSmem L = pt_layout();
   const int N = a.N, M = a.M, T = a.T, t = a.t, Dx = a.Dx;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP;
@@ -339,7 +341,7 @@ size_t ffbsi_pair_tc_image_bytes(int B, int N) { return (size_t)B * ((N + kPtCol
 int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
   {
     ProfScope ps_(PK_FFBSI, st);
-    ffbsi_pair_prep_kernel<<<dim3((a.N + 127) / 128, a.B), 128, 0, st>>>(a);
+    PSVO_CUDA(launch_pdl(ffbsi_pair_prep_kernel, dim3((a.N + 127) / 128, a.B), dim3(128), 0, st, pdl_enabled(), a));
     PSVO_LAUNCH_CHECK();
   }
   const PtSmem L = pt_layout();
@@ -350,7 +352,7 @@ int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
   const long long work = (long long)a.B * (((ncand + 127) / 128 + kPtGroups - 1) / kPtGroups);
   const int grid = (int)(work < num_sms() ? work : num_sms());
   ProfScope ps_(PK_FFBSI, st);
-  ffbsi_pair_tc_kernel<<<grid, kPtThreads, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(ffbsi_pair_tc_kernel, dim3(grid), dim3(kPtThreads), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }

@@ -1,5 +1,6 @@
 // psvo_common.cuh -- host-side error plumbing and block-level device primitives.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -121,9 +122,16 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+// PSVO_PDL=0 switches programmatic dependent launches off (plain stream order everywhere)
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("PSVO_PDL") != nullptr && getenv("PSVO_PDL")[0] == '0');
+  return on;
+}
 #if defined(__CUDACC__)
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// entry of a small kernel inside a launch-latency-bound loop: let the next launch be scheduled, then wait for the previous kernel
+__device__ __forceinline__ void griddep_entry() { griddep_launch_dependents(); griddep_wait(); }
 #endif
 
 }  // namespace psvo

@@ -59,6 +59,7 @@ __device__ __forceinline__ float particle_weight_grad(const BwdArgs& a, int b, i
 template <int DXP, int DYP>
 __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  griddep_entry();
   const int Dx = a.Dx, Dy = a.Dy, N = a.N;
   const bool poisson = a.flags & PSVO_F_POISSON;
   MlpS<DXP, DYP> gs;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
 template <int DXP>
 __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  griddep_entry();
   const int Dx = a.Dx, N = a.N;
   const bool two_q = a.flags & PSVO_F_TWO_Q, boot = a.flags & PSVO_F_BOOTSTRAP;
   const bool t0 = a.t == 0;
@@ -481,7 +483,7 @@ static int launch_emission_t(const BwdArgs& a, int block, int grid, size_t smem,
     configured = smem;
   }
   ProfScope ps_(PK_BWD, st);
-  kern<<<grid, block, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }
@@ -494,7 +496,7 @@ static int launch_proposal_t(const BwdArgs& a, int block, int grid, size_t smem,
     configured = smem;
   }
   ProfScope ps_(PK_BWD, st);
-  kern<<<grid, block, smem, st>>>(a);
+  PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
   return 0;
 }
