@@ -87,7 +87,7 @@ int check_dims(const psvo_dims* d) {
   return 0;
 }
 
-struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; unsigned char* tc_image; size_t bytes; };
+struct FwdWs { float *sig, *mu2_all, *mu0, *muf0, *logWbar; unsigned char* tc_image; int* tc_sync; size_t bytes; };
 
 FwdWs carve_fwd(const psvo_dims* d, void* ws) {
   FwdWs w;
@@ -100,6 +100,7 @@ FwdWs carve_fwd(const psvo_dims* d, void* ws) {
   w.muf0 = take((size_t)d->B * d->Dx);
   w.logWbar = take((size_t)d->B * d->N);
   w.tc_image = reinterpret_cast<unsigned char*>(take(32 * 1024));      // 128 KB: fp16 weight image of the tensor-core path
+  w.tc_sync = reinterpret_cast<int*>(take(tc_filter_sync_bytes(d->B) / sizeof(float)));   // per-sequence flags of the persistent tensor-core filter
   w.bytes = off;
   return w;
 }
@@ -179,7 +180,11 @@ PSVO_API int psvo_smc_forward_path(const psvo_dims* d, const psvo_params* p) {
   pa.N = d->N; pa.B = d->B; pa.T = d->T; pa.Dx = d->Dx; pa.Dy = d->Dy; pa.t = 0; pa.flags = d->flags;
   pa.tc_image = nullptr;
   const PropPlan plan = plan_propagate(pa);
-  if (tc_propagate_supported(pa)) return 2;
+  if (tc_propagate_supported(pa)) {
+    pa.tc_image = reinterpret_cast<const unsigned char*>(p);        // any non-null value: only the shape is examined here
+    ResampleArgs ra; ra.N = d->N; ra.B = d->B; ra.T = d->T; ra.flags = d->flags;
+    return tc_filter_persistent_supported(pa, ra) ? 3 : 2;
+  }
   size_t psm = 0; int pblk = 0;
   return persistent_filter_supported(pa, plan, &psm, &pblk) ? 1 : 0;
 }
@@ -235,6 +240,13 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
   // tensor-core path: the ancestor gather X_anc[t] = Xs[t][anc[t]] is folded into the propagate launch of t+1 (which
   // needs the parents anyway), so only the last step's resample launch moves particle states
   const bool fuse_gather = pa.tc_image != nullptr;
+  if (tc_filter_persistent_supported(pa, ra)) {
+    // the whole filter in ONE launch; only the last step's resampling (the one that gathers X_anc itself) is a launch of its own
+    pa.X_anc_w = X_anc;
+    if (int e = launch_filter_tc_persistent(pa, ra, w.tc_sync, st)) return e;
+    ra.t = d->T - 1; ra.skip_gather = 0; ra.pdl = 0;
+    return launch_resample(ra, st);
+  }
   for (int t = 0; t < d->T; ++t) {
     pa.t = t; ra.t = t;
     pa.anc_prev = fuse_gather && t > 0 ? anc : nullptr; pa.X_anc_w = X_anc;

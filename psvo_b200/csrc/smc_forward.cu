@@ -15,6 +15,7 @@
 #include "mlp_tile.cuh"
 #include <cstdlib>
 #include "smc_kernels.h"
+#include "resample_group.cuh"
 
 namespace psvo {
 
@@ -569,6 +570,39 @@ __global__ void __launch_bounds__(1024) smc_resample_kernel(ResampleArgs a, int 
   resample_body<true>(a, blockIdx.x, blockIdx.y, gridDim.y, a.t, smraw, sscr, fscr, sG, kbits);
 }
 
+// One CTA of 1024 threads per sequence, thread-contiguous decomposition (resample_group.cuh): every thread owns a contiguous
+// run of N / 1024 particles, so the CDF and the guide table need one shuffle scan per WARP instead of one per 32 particles,
+// and the cross-warp step is a second shuffle scan every warp does for itself -- about half the instructions of
+// resample_body and six block barriers.  Same indices bit for bit (integer sums do not depend on their grouping).
+__global__ void __launch_bounds__(1024) smc_resample_lean_kernel(ResampleArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  griddep_launch_dependents();               // the next propagate launch may stage its weights while this kernel runs
+  griddep_wait();                            // log_W_t / X_t of the propagate launch before this one
+  const int b = blockIdx.x, t = a.t, N = a.N, Dx = a.Dx;
+  resample_lean<1024, false>(a, b, t, smraw, threadIdx.x, RgBlockBar{});
+  if (a.skip_gather) return;
+  __syncthreads();                           // this block's ancestor indices are in global memory: read them back through L2
+  const size_t bt = (size_t)b * a.T + t;
+  const int* anc = a.anc + bt * N;
+  const float* Xt = a.Xs + bt * N * Dx;
+  float* Xa = a.X_anc + bt * N * Dx;
+  if ((Dx & 3) == 0) {
+    const int v4 = Dx >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(Xt);
+    float4* dst4 = reinterpret_cast<float4*>(Xa);
+    const int pieces = N * v4;
+    for (int q = threadIdx.x; q < pieces; q += blockDim.x) {
+      const int c = q / v4, v = q - c * v4;
+      dst4[q] = __ldg(src4 + (size_t)__ldcg(anc + c) * v4 + v);
+    }
+  } else {
+    for (int q = threadIdx.x; q < N * Dx; q += blockDim.x) {
+      const int c = q / Dx, d = q - c * Dx;
+      Xa[q] = Xt[(size_t)__ldcg(anc + c) * Dx + d];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Persistent whole-filter kernel: ONE launch per forward pass, one CTA per sequence looping over time.
 // For small particle counts / few sequences (BASELINE configs 1-4: B = 1 chains, the reference's own operating
@@ -692,6 +726,22 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   if (a.skip_gather && (size_t)N * 16 <= 220 * 1024) {
     parts = 1;
     while (parts < 4 && (long long)a.B * parts * 2 < num_sms() && N / (parts * 2) >= 512) parts *= 2;
+  }
+  {
+    // big particle sets with one CTA per sequence: the thread-contiguous kernel (PSVO_RESAMPLE_LEAN=0 keeps the older one)
+    static const bool lean_off = getenv("PSVO_RESAMPLE_LEAN") != nullptr && getenv("PSVO_RESAMPLE_LEAN")[0] == '0';
+    const size_t lsm = rg_smem_bytes(N, 1024);
+    if (!lean_off && parts == 1 && N >= 2048 && lsm <= 220 * 1024) {
+      static size_t lean_configured = 0;
+      if (lsm > 40 * 1024 && lsm > lean_configured) {
+        PSVO_CUDA(cudaFuncSetAttribute(smc_resample_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+        lean_configured = lsm;
+      }
+      ProfScope ps_(PK_RESAMPLE, st);
+      PSVO_CUDA(launch_pdl(smc_resample_lean_kernel, dim3(a.B), dim3(1024), lsm, st, a.pdl != 0, a));
+      PSVO_LAUNCH_CHECK();
+      return 0;
+    }
   }
   const int chunk = (N + parts - 1) / parts;
   int block = N >= 4096 ? (a.skip_gather ? 1024 : 512) : (N >= 1024 ? 256 : (N >= 256 ? 128 : (N > 32 ? 64 : 32)));

@@ -93,6 +93,21 @@ size_t tc_image_bytes(const PropArgs& a);
 int launch_tc_stage_image(const PropArgs& a, unsigned char* image, cudaStream_t st);
 int launch_propagate_tc(const PropArgs& a, cudaStream_t st);
 
+// persistent tensor-core filter: ALL time steps of the forward filter in one cooperative launch; the resampling of steps
+// 0..T-2 runs inside it (one worker warp per CTA, per-sequence flags in global memory), the caller launches the ordinary
+// resampling kernel for step T-1 (the only one that gathers X_anc itself)
+struct TcPersistArgs {
+  ResampleArgs ra;
+  int* cnt;                // (B) tiles stored per sequence, all steps; zeroed by the launcher
+  int* ready;              // (B) resampled steps per sequence
+  int* err;                // watchdog flag
+  int* next;               // tile counter: tiles are handed out in (t, b, tile) order
+  unsigned rs_smem_off;    // byte offset of the worker's region in dynamic shared memory
+};
+bool tc_filter_persistent_supported(const PropArgs& a, const ResampleArgs& ra);
+size_t tc_filter_sync_bytes(int B);
+int launch_filter_tc_persistent(PropArgs a, const ResampleArgs& ra, int* sync, cudaStream_t st);
+
 // tensor-core (tcgen05) MLP f and MLP g of every FFBSi candidate (smc_propagate_tc.cu); weight image from
 // launch_tc_stage_image with PropArgs.q1 = the f network
 struct CandTcArgs {

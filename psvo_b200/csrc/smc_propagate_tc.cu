@@ -27,6 +27,7 @@
 #include "mlp_tile.cuh"
 #include "smc_kernels.h"
 #include "tc_common.cuh"
+#include "resample_group.cuh"
 
 namespace psvo {
 
@@ -47,10 +48,30 @@ extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_trace(long l
 #define TC_TRACE_INIT() do { } while (0)
 #endif
 
+#ifdef PSVO_TC_PSTATS
+// per-group cycle accounting of the persistent filter kernel (thread 0 of every compute group): 8 counters per group
+//   0 wait for ready[b] | 1 tile body | 2 tile-end bookkeeping (barriers, atomics) | 3 lock wait | 4 resampling | 5 tiles | 6 resamplings
+__device__ long long* g_tc_pstats = nullptr;
+extern "C" __attribute__((visibility("default"))) int psvo_debug_tc_pstats(long long* buf) {
+  cudaMemcpyToSymbol(g_tc_pstats, &buf, sizeof(buf));
+  return 0;
+}
+#define PSTAT_DECL() long long ps_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64()
+#define PSTAT(k) do { const long long n_ = clock64(); ps_[k] += n_ - pc_; pc_ = n_; } while (0)
+#define PSTAT_INC(k) do { ps_[k] += 1; } while (0)
+#define PSTAT_DUMP(grp) do { if ((threadIdx.x & 127) == 0 && g_tc_pstats != nullptr) for (int k_ = 0; k_ < 8; ++k_) g_tc_pstats[(blockIdx.x * 4 + (grp)) * 8 + k_] = ps_[k_]; } while (0)
+#else
+#define PSTAT_DECL() do { } while (0)
+#define PSTAT(k) do { } while (0)
+#define PSTAT_INC(k) do { } while (0)
+#define PSTAT_DUMP(grp) do { } while (0)
+#endif
+
 constexpr int kTcGroups = 4;
 constexpr int kTcChunk = 16;           // hidden units per pipeline stage = one K-step of layer 2
 constexpr int kTcBufs = 4;             // layer-1 accumulators per group
 constexpr int kTcThreads = kTcGroups * 128 + kTcGroups * 32;
+constexpr int kTcConsts = 160;                 // floats of one set of per-step constants (t = 0 | t > 0)
 constexpr int kTcBars = 12;            // mbarriers per group
 // exact power-of-two operand scales: W1 (and its bias) by 2^4, W2 by 2^8 -> their fp16 lo halves stay normal; the hidden
 // activations travel in 16x units (|h| < 4094) and the layer-2 accumulator in 4096x units, undone in the output FFMA
@@ -91,7 +112,7 @@ __host__ __device__ inline TcPropSmem tc_prop_layout(int H, int NPG) {
   s.w1g_hi = PSVO_TAKE(H * 16 * 2); s.w1g_lo = PSVO_TAKE(H * 16 * 2); s.w1g_b = PSVO_TAKE(H * 16 * 2);
   s.w2g_hi = PSVO_TAKE(NPG * H * 2); s.w2g_lo = PSVO_TAKE(NPG * H * 2);
   s.b2q = PSVO_TAKE(16 * 4); s.b2g = PSVO_TAKE(32 * 4);
-  s.consts = PSVO_TAKE(160 * 4);
+  s.consts = PSVO_TAKE(2 * kTcConsts * 4);
   s.rowc = PSVO_TAKE(kTcGroups * 2 * 64 * 4);
   s.bars = PSVO_TAKE(kTcBars * kTcGroups * 8); s.slot = PSVO_TAKE(16);
 #undef PSVO_TAKE
@@ -268,11 +289,13 @@ __device__ __forceinline__ void tc_issue_l2(const TcNetAddr& na, uint32_t tD1, u
 // L2(c)'s completion instead would put ~300 cycles into every one of the 64 events of a tile (PSVO_TC_WAR_WAIT=1 builds that
 // conservative variant; it was the slower one by 25 %).
 // par: bit 0 = A1, bits 1-4 = full[0..3], bit 5 = L2
-template <int NP>
+template <int NP, bool WAIT_A1 = true>
 __device__ __forceinline__ void tc_mma_net(const TcNetAddr& na, uint32_t lbo1, uint32_t tb, uint32_t bars, int nst, uint32_t& par) {
   TC_TRACE(10);
-  mbar_wait_u32(bars + 8 * kBarA1, par & 1u); par ^= 1u;
-  tc::fence_after_sync();
+  if (WAIT_A1) {
+    mbar_wait_u32(bars + 8 * kBarA1, par & 1u); par ^= 1u;
+    tc::fence_after_sync();
+  }
   TC_TRACE(11);
   if (tc::elect_one()) {
 #pragma unroll
@@ -313,9 +336,11 @@ __device__ __forceinline__ void tc_mma_net(const TcNetAddr& na, uint32_t lbo1, u
   }
 }
 
-// MMA-issuing warp of group `grp`: every tile of the group, networks first_net..1
-template <int NPG>
-__device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, const TcPropSmem& L, int H, int grp, int work, int nst, int first_net) {
+// MMA-issuing warp of group `grp`: every tile of the group, networks first_net..1.  items = tiles of the launch (static stride);
+// the persistent whole-filter kernel hands tiles out dynamically and tells this warp per tile what to run (see below)
+template <int NPG, bool PERSIST = false>
+__device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, const TcPropSmem& L, int H, int grp, int items, int nst, int first_net,
+                                            int work = 0) {
   const uint32_t bars = tc_opaque(sm_base + L.bars + 8u * kTcBars * grp);
   const uint32_t tb = tc_opaque(tmem + grp * 128);
   const uint32_t lbo1 = tc_opaque((uint32_t)H * 16u);
@@ -325,7 +350,26 @@ __device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, con
   ag.w1h = tc_opaque(sm_base + L.w1g_hi); ag.w1l = tc_opaque(sm_base + L.w1g_lo); ag.w1b = tc_opaque(sm_base + L.w1g_b);
   ag.w2h = tc_opaque(sm_base + L.w2g_hi); ag.w2l = tc_opaque(sm_base + L.w2g_lo);
   uint32_t par = 0;
-  for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+  if (PERSIST) {
+    // tiles are handed out dynamically: the compute group leaves a command word next to its first operand (published by the
+    // A1 barrier's release / acquire): 0 = both networks, 1 = emission network only (t = 0), 2 = no more tiles
+    const uint32_t cmd_addr = tc_opaque(sm_base + (uint32_t)work);         // `work` carries the shared-memory offset of the group's word
+    for (;;) {
+      mbar_wait_u32(bars + 8 * kBarA1, par & 1u); par ^= 1u;
+      tc::fence_after_sync();
+      uint32_t cmd;
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(cmd) : "r"(cmd_addr) : "memory");
+      if (cmd == 2u) break;
+      if (cmd == 0u) {
+        tc_mma_net<16, false>(aq, lbo1, tb, bars, nst, par);
+        tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
+      } else {
+        tc_mma_net<NPG, false>(ag, lbo1, tb, bars, nst, par);
+      }
+    }
+    return;
+  }
+  for (int wi = blockIdx.x * kTcGroups + grp; wi < items; wi += gridDim.x * kTcGroups) {
     if (first_net == 0) tc_mma_net<16>(aq, lbo1, tb, bars, nst, par);
     tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
   }
@@ -403,12 +447,41 @@ __device__ __forceinline__ void tc_group_init(TcGroup& g, const TcCtx& cx, int g
   tc::tmem_st_wait();
 }
 
-template <int NPG>
-__global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArgs a) {
-  extern __shared__ __align__(128) unsigned char sm[];
+// One body, two kernels.  PERSIST = false: one time step per launch (a.t), 640 threads.  PERSIST = true: the WHOLE filter in one
+// launch -- every group walks the tiles of all T steps in one global order (item = t * work + tile; a group takes every
+// (gridDim * 4)-th item, so the 7-vs-6 tiles-per-group imbalance of a single step averages out), weights / TMEM / barriers are set
+// up once, and the step boundary is replaced by per-sequence flags in global memory:
+//   cnt[b]   += 1 (acq_rel) when a group has stored a tile of sequence b.  The group whose increment completes step t of the
+//              sequence (cnt[b] = tiles_per_seq * (t + 1)) resamples (b, t) right away (resample_group.cuh: 128 threads,
+//              ~16 k warp-instructions, a quarter of the 1024-thread kernel's) in the CTA's one CDF region (shared-memory
+//              lock), then ready[b] = t + 1 (release)
+//   a tile of (b, t >= 1) starts with an acquire load of ready[b] >= t
+// so the resampling of a sequence overlaps the propagation of all the others instead of owning the machine between two launches.
+// (Every register of the SM belongs to the 16 compute + 4 issuing warps -- 4 x 112 + 32 = 480 of the 512 per scheduler that a
+// launch can allocate -- so a dedicated resampling warp would have to take its registers from the compute warps.)
+// No grid-wide barrier.  Progress: an item depends only on items with smaller numbers (directly, or through the resampling its
+// owner group runs after it), every group handles its items in increasing order, the lock is only held across a resampling,
+// which waits for nothing, and all CTAs are co-resident (cooperative launch).
+// A bounded spin (PSVO watchdog) turns a protocol bug into NaN objectives instead of a hung GPU.
+struct TcWait {
+  int* err; bool dead;
+  __device__ __forceinline__ void until(const int* flag, int target) {
+    if (dead) return;
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) < target) {
+      __nanosleep(64);
+      if ((++spins & 1023u) == 0u && (spins > (1u << 23) || *reinterpret_cast<volatile int*>(err) != 0)) {
+        *reinterpret_cast<volatile int*>(err) = 1; dead = true; return;
+      }
+    }
+  }
+};
+
+template <int NPG, bool PERSIST>
+__device__ __forceinline__ void tc_prop_body(const PropArgs& a, const TcPersistArgs* pp, unsigned char* sm) {
   const int Dx = a.Dx, Dy = a.Dy, N = a.N, H = a.g.width[0];
   const bool two_q = a.flags & PSVO_F_TWO_Q, poisson = a.flags & PSVO_F_POISSON;
-  const bool t0 = a.t == 0;
+  const bool t0_launch = a.t == 0;
   const TcPropSmem L = tc_prop_layout(H, NPG);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform (kept in a uniform register)
@@ -419,55 +492,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
   // consts: s1[16] | sp[16] | inv1[16] | inv2[16] | inv_sp[16] | inv_s1[16] | inv_sg[32] | ld_p ld_f ld_g
   float* C = reinterpret_cast<float*>(sm + L.consts);
   tc_setup_begin(sm, L, a.tc_image, tid, warp);
-  if (tid < 16) {
-    const int d = tid;
-    const float s1 = a.sig[(t0 ? SIG_Q0 : SIG_Q1) * 32 + d], s2 = a.sig[SIG_Q2 * 32 + d];
+  // set 0: the launch's step (PERSIST: t = 0), set 1 (PERSIST only): t > 0
+  if (tid < 16 || (PERSIST && tid >= 64 && tid < 80)) {
+    const int d = tid & 15, set = tid >> 6;
+    const bool first = PERSIST ? set == 0 : t0_launch;
+    float* Cs = C + set * kTcConsts;
+    const float s1 = a.sig[(first ? SIG_Q0 : SIG_Q1) * 32 + d], s2 = a.sig[SIG_Q2 * 32 + d];
     const float i1 = 1.0f / s1, i2 = 1.0f / s2;
     const float spv = two_q ? 1.0f / (i1 + i2) : s1;
-    C[d] = s1; C[16 + d] = spv; C[32 + d] = i1; C[48 + d] = i2; C[64 + d] = 1.0f / spv; C[80 + d] = i1;
+    Cs[d] = s1; Cs[16 + d] = spv; Cs[32 + d] = i1; Cs[48 + d] = i2; Cs[64 + d] = 1.0f / spv; Cs[80 + d] = i1;
   }
-  if (tid >= 32 && tid < 64) C[96 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
+  if ((tid >= 32 && tid < 64) || (PERSIST && tid >= 96 && tid < 128)) {
+    const int d = tid & 31, set = tid >> 6;
+    C[set * kTcConsts + 96 + d] = d < Dy ? 1.0f / a.sig[SIG_G * 32 + d] : 0.0f;   // 0 beyond Dy: padded columns drop out
+  }
   TC_TRACE_INIT();
   TcCtx tcx;
   tc_setup_finish<NPG>(sm, L, H, tcx);
-  if (tid == 0) {
+  if (tid == 0 || (PERSIST && tid == 64)) {
+    float* Cs = C + (tid >> 6) * kTcConsts;
     float lp = 0.f, lf = 0.f, lg = 0.f;
-    for (int d = 0; d < Dx; ++d) { lp += logf(C[16 + d]); lf += logf(C[d]); }
+    for (int d = 0; d < Dx; ++d) { lp += logf(Cs[16 + d]); lf += logf(Cs[d]); }
     if (!poisson) for (int d = 0; d < Dy; ++d) lg += logf(a.sig[SIG_G * 32 + d]);
-    C[128] = lp; C[129] = lf; C[130] = lg;
+    Cs[128] = lp; Cs[129] = lf; Cs[130] = lg;
   }
   __syncthreads();
   const int tiles_per_seq = (N + 127) / 128;
   const int work = a.B * tiles_per_seq;
+  const int items = PERSIST ? work * a.T : work;                         // < 2^31 (checked by the launcher)
 
   // programmatic dependent launch: everything above (weight image, barriers, TMEM) ran while the previous kernel (the resampling
   // of step t-1) was still draining; the next kernel may start its own prologue from here on, and the first read of anything the
   // previous kernel wrote (ancestors) comes after griddep_wait()
-  griddep_launch_dependents();
+  if (!PERSIST) griddep_launch_dependents();
   if (warp >= kTcGroups * 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");                // 128 x (96 - 32) registers released = exactly the 512 x (112 - 96) the compute warps take
-    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, t0 ? 1 : 0);
+    tc_mma_warp<NPG, PERSIST>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, items, nchunk, t0_launch ? 1 : 0,
+                              PERSIST ? (int)(pp->rs_smem_off + 4u * (12 + warp - kTcGroups * 4)) : 0);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
-    griddep_wait();
+    if (!PERSIST) griddep_wait();
     // =================================== compute groups ===================================
     const int grp = warp >> 2;
-    const float* s1 = C; const float* sp = C + 16; const float* inv1 = C + 32; const float* inv2 = C + 48;
-    const float* inv_sp = C + 64; const float* inv_s1 = C + 80; const float* inv_sg = C + 96;
-    const float ld_p = C[128], ld_f = C[129], ld_g = C[130];
+    const float* inv_sg = C + 96;                                          // the emission constants do not depend on the step
+    const float ld_g = C[130];
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     const float neg_logN = -logf((float)N);
-    (void)s1;
+    TcWait wt{PERSIST ? pp->err : nullptr, false};
     TcGroup g;
     const int gt = tid & 127;
     tc_group_init(g, tcx, grp, warp);
 
     uint32_t tile_it = 0;
-    for (int wi = blockIdx.x * kTcGroups + grp; wi < work; wi += gridDim.x * kTcGroups) {
+    // PERSIST: region header words: 0 lock | 1..4 "this group resamples" | 8..11 the group's next item | 12..15 command word of
+    // the group's MMA warp.  Items are handed out by a global counter, and a group only takes its next one when it is free to
+    // start it: a tile held across a resampling would finish last in ITS sequence, make this group resample that one too, and so
+    // on (measured: chains of tile + resampling per group, every sequence they touch late by two resamplings)
+    int* rg = PERSIST ? reinterpret_cast<int*>(sm + pp->rs_smem_off) : nullptr;
+    int item = blockIdx.x * kTcGroups + grp;
+    if (PERSIST) {
+      if (gt == 0) rg[8 + grp] = atomicAdd(pp->next, 1);
+      rg_bar(1 + grp);
+      item = rg[8 + grp];
+    }
+    PSTAT_DECL();
+    for (; item < items; item += PERSIST ? 0 : gridDim.x * kTcGroups) {
+      const int t = PERSIST ? item / work : a.t;
+      const int wi = PERSIST ? item - t * work : item;
+      const bool t0 = t == 0;
+      if (PERSIST && gt == 0) rg[12 + grp] = t0 ? 1 : 0;
+      const float* Cs = C + ((PERSIST && !t0) ? kTcConsts : 0);
+      const float* sp = Cs + 16; const float* inv1 = Cs + 32; const float* inv2 = Cs + 48;
+      const float* inv_sp = Cs + 64; const float* inv_s1 = Cs + 80;
+      const float ld_p = Cs[128], ld_f = Cs[129];
       const int b = wi / tiles_per_seq;
       const int n = (wi - b * tiles_per_seq) * 128 + gt;
       const bool live = n < N;
-      const size_t bt = (size_t)b * a.T + a.t;
+      const size_t bt = (size_t)b * a.T + t;
+      PSTAT(2);
+      if (PERSIST && !t0) wt.until(pp->ready + b, t);                      // (b, t-1) resampled: its ancestors are visible (acquire)
+      PSTAT(0);
       const size_t row = bt * N + (live ? n : 0);
 
       TC_TRACE(20);
@@ -485,7 +589,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       const float* xsrc = nullptr;
       if (!t0) {
         const size_t prow = (bt - 1) * N + (live ? n : 0);
-        xsrc = a.anc_prev != nullptr ? a.Xs + ((bt - 1) * N + __ldg(a.anc_prev + prow)) * Dx : a.X_anc + prow * Dx;
+        xsrc = a.anc_prev != nullptr ? a.Xs + ((bt - 1) * N + (PERSIST ? __ldcg(a.anc_prev + prow) : __ldg(a.anc_prev + prow))) * Dx : a.X_anc + prow * Dx;
       }
       // noise for this particle (the Philox work also covers the latency of the ancestor index load above)
       float e[16];
@@ -494,7 +598,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
 #pragma unroll
         for (int d = 0; d < 16; ++d) e[d] = d < Dx ? src[d] : 0.0f;
       } else {
-        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n : 0);
+        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + (live ? n : 0);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
@@ -514,7 +618,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
         }
       }
       if (a.eps == nullptr) {
-        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + a.t) * N + (live ? n : 0);
+        const uint64_t gidx = ((uint64_t)(a.seq_offset + b) * a.T + t) * N + (live ? n : 0);
 #pragma unroll
         for (int c = 2; c < 4; ++c) {
           if (4 * c < Dx) normal4(philox4x32_10(a.seed, gidx, c, 0u), &e[4 * c]);
@@ -618,12 +722,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArg
       float lwb = neg_logN;
       if (!t0 && a.logWbar != nullptr && live) lwb = a.logWbar[(size_t)b * N + n];
       if (live) a.log_Ws[bt * N + n] = ((f_lp + g_lp) - q_lp) + lwb;
+      if (PERSIST) {
+        // tile stored: the group's barrier orders the 128 threads' stores before thread 0's acq_rel increment (cumulative at
+        // gpu scope).  Whoever completes the step of the sequence resamples it -- the whole group, ~16 k warp-instructions
+        // (t = T-1 is left to the resampling launch that follows the kernel: it also gathers X_anc[T-1])
+        PSTAT(1); PSTAT_INC(5);
+        rg_bar(1 + grp);
+        if (gt == 0) {
+          const int last = t + 1 < a.T && atom_add_acq_rel_gpu(pp->cnt + b, 1) + 1 == tiles_per_seq * (t + 1);
+          rg[1 + grp] = last;
+          if (!last) rg[8 + grp] = atomicAdd(pp->next, 1);
+        }
+        rg_bar(1 + grp);
+        if (rg[1 + grp]) {
+          PSTAT(2);
+          if (gt == 0) while (atomicCAS(rg, 0, 1) != 0) __nanosleep(200);
+          rg_bar(1 + grp);
+          PSTAT(3);
+          resample_group(pp->ra, b, t, sm + pp->rs_smem_off, gt, 1 + grp);
+          rg_bar(1 + grp);                                                 // the group's ancestor stores happen before thread 0's release
+          PSTAT(4); PSTAT_INC(6);
+          if (gt == 0) {
+            st_release_gpu(pp->ready + b, t + 1);
+            __threadfence_block();
+            atomicExch(rg, 0);
+            rg[8 + grp] = atomicAdd(pp->next, 1);
+          }
+          rg_bar(1 + grp);
+        }
+        item = rg[8 + grp];
+      }
+    }
+    PSTAT_DUMP(grp);
+    if (PERSIST) {                                                         // no more tiles: release the group's MMA warp
+      if (gt == 0) rg[12 + grp] = 2;
+      mbar_arrive_u32(g.bar + 8 * kBarA1);
     }
   }
 
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tcx.tmem, 512);
+}
+
+template <int NPG>
+__global__ void __launch_bounds__(kTcThreads, 1) smc_propagate_tc_kernel(PropArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  tc_prop_body<NPG, false>(a, nullptr, sm);
+}
+template <int NPG>
+__global__ void __launch_bounds__(kTcThreads, 1) smc_filter_tc_persistent_kernel(PropArgs a, TcPersistArgs p) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  if (threadIdx.x < 16) reinterpret_cast<int*>(sm + p.rs_smem_off)[threadIdx.x] = 0;  // the CDF region's lock and flags (published by the prologue's barriers)
+  tc_prop_body<NPG, true>(a, &p, sm);
+  if (threadIdx.x == 0 && *reinterpret_cast<volatile int*>(p.err) != 0)          // watchdog fired somewhere: poison the objective
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) p.ra.logZ_b[b] = __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -962,6 +1115,53 @@ int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
     if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)); cfg = true; }
     PSVO_CUDA(launch_pdl(smc_propagate_tc_kernel<32>, dim3(grid), dim3(kTcThreads), smem, st, a.pdl != 0, a));
   }
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- persistent whole-filter launch ------------------------------------------------------------------------------------
+// opt-in (PSVO_TC_PERSIST=1): measured slower than per-step launches at the config-5 shard (the chain
+// tile -> resampling -> next step's tile of a sequence is longer than the step period once the resampling competes with
+// sixteen other warps for issue slots)
+static bool tc_persist_env() {
+  static const bool on = getenv("PSVO_TC_PERSIST") != nullptr && getenv("PSVO_TC_PERSIST")[0] == '1';
+  return on;
+}
+size_t tc_filter_sync_bytes(int B) { return align_up(((size_t)2 * B + 32) * sizeof(int), 256); }
+
+bool tc_filter_persistent_supported(const PropArgs& a, const ResampleArgs& ra) {
+  if (!tc_persist_env() || a.tc_image == nullptr || !tc_propagate_supported(a)) return false;
+  // resampling on (IWAE keeps its per-particle log Wbar in a buffer that is rewritten every step: per-step launches), at
+  // least two steps, and the worker's CDF / guide table must fit next to the weight image
+  if (!(a.flags & PSVO_F_RESAMPLE) || a.T < 2 || a.N < 128) return false;
+  if ((long long)a.B * ((a.N + 127) / 128) * a.T >= (1LL << 31)) return false;
+  (void)ra;
+  const TcPropSmem L = tc_prop_layout(a.g.width[0], 32);
+  return L.total + 256 + rg_smem_bytes(a.N) <= 227 * 1024;
+}
+
+int launch_filter_tc_persistent(PropArgs a, const ResampleArgs& ra, int* sync, cudaStream_t st) {
+  PSVO_REQUIRE(tc_filter_persistent_supported(a, ra) && sync != nullptr, "persistent tensor-core filter: unsupported shape");
+  const TcPropSmem L = tc_prop_layout(a.g.width[0], 32);
+  TcPersistArgs p;
+  p.ra = ra; p.ra.t = 0; p.ra.skip_gather = 1;
+  p.cnt = sync; p.ready = sync + a.B; p.err = sync + 2 * a.B; p.next = sync + 2 * a.B + 1;
+  p.rs_smem_off = (L.total + 255u) & ~127u;
+  const size_t smem = (size_t)p.rs_smem_off + rg_smem_bytes(a.N);
+  const int tiles = a.B * ((a.N + 127) / 128);
+  int grid = (tiles + kTcGroups - 1) / kTcGroups;
+  if (grid > num_sms()) grid = num_sms();
+  a.t = 0; a.anc_prev = ra.anc; a.logWbar = nullptr;
+  PSVO_CUDA(cudaMemsetAsync(sync, 0, tc_filter_sync_bytes(a.B), st));
+  ProfScope ps_(PK_PROP, st);
+  PSVO_CUDA(cudaFuncSetAttribute(smc_filter_tc_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;           // co-residency of all CTAs is part of the protocol: let the runtime check it
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  PSVO_CUDA(cudaLaunchKernelEx(&cfg, smc_filter_tc_persistent_kernel<32>, a, p));
   PSVO_LAUNCH_CHECK();
   return 0;
 }
