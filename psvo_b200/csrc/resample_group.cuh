@@ -59,19 +59,21 @@ struct RgBlockBar {            // the whole CTA
 };
 __device__ __forceinline__ void rg_bar(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
 
-// sequence b, time t; NT threads (g = thread index, bar = their barrier).  Writes anc[b][t][:], lse[b][t], accumulates logZ_b[b]
-// (and logWbar when resampling is off).  LDCG: log_Ws[b][t][:] was written by other SMs during this launch -> read through L2.
+// sequence b, time t; NT threads (a multiple of 32; g = thread index, bar = their barrier).  Writes anc[b][t][:], lse[b][t],
+// accumulates logZ_b[b] (and logWbar when resampling is off); sAnc (optional, N ints of shared memory) also receives the
+// ancestors for a gather by the caller.  LDCG: log_Ws[b][t][:] was written by other SMs during this launch -> read through L2.
 // region: rg_smem_bytes(N, NT) bytes; the caller owns the first 64 bytes (lock, flags).
-template <int NT, bool LDCG, typename Bar>
-__device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int t, unsigned char* region, int g, Bar bar) {
-  constexpr int NW = NT / 32;
+template <bool LDCG, typename Bar>
+__device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int t, unsigned char* region, int g, const int NT, Bar bar,
+                                              int* sAnc = nullptr) {
+  const int NW = NT >> 5;
   const int N = a.N;
   const int lane = g & 31, w = g >> 5;
   const int sh = rg_chunk_shift(N, NT), cl = 1 << sh;
   const int kbits = rg_guide_bits(N, NT), K = 1 << kbits;
-  int ntb = 0;
-  while ((1 << ntb) < NT) ++ntb;
-  const int gsh = kbits - ntb, gl = 1 << gsh, gs = 24 - kbits;
+  int ntb = 5;                                             // the guide table is scanned by the first VT = 2^ntb <= NT threads
+  while ((2 << ntb) <= NT) ++ntb;
+  const int VT = 1 << ntb, gsh = kbits - ntb, gl = 1 << gsh, gs = 24 - kbits;
   // region header (1 KB): words 0..15 belong to the caller | 64: NW warp maxima | 256: NW warp totals of the weights, then the
   // grand total | 768: NW warp totals of the histogram
   float* sred = reinterpret_cast<float*>(region + 64);
@@ -100,13 +102,7 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
   mx = warp_max(mx);
   if (lane == 0) sred[w] = mx;
   bar();
-  if (NW <= 4) {
-    mx = sred[0];
-#pragma unroll
-    for (int k = 1; k < NW; ++k) mx = fmaxf(mx, sred[k]);
-  } else {
-    mx = warp_max(lane < NW ? sred[lane] : -INFINITY);
-  }
+  mx = warp_max(lane < NW ? sred[lane] : -INFINITY);
 
   // ---- integer CDF: serial running sum over this thread's contiguous run, shuffle scan of the thread totals, warp totals
   //      through shared memory, offsets added back
@@ -123,11 +119,7 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
   if (lane == 31) sws[w] = inc;
   bar();
   unsigned long long total, off = inc - run;
-  if (NW <= 4) {
-    total = 0ull;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) { const unsigned long long wk = sws[k]; if (k < w) off += wk; total += wk; }
-  } else {
+  {
     // every warp scans the NW warp totals itself (one shuffle scan; no extra barrier)
     const unsigned long long wt = lane < NW ? sws[lane] : 0ull;
     unsigned long long winc = wt;
@@ -165,23 +157,22 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
     }
     bar();
     const int g_lo = g * gl;
-    int tot = 0;
+    int tot = 0, ginc = 0;
+    if (g < VT) {
 #pragma unroll 4
-    for (int i = 0; i < gl; ++i) tot += sG[g_lo + i + g];
-    int ginc = tot;
+      for (int i = 0; i < gl; ++i) tot += sG[g_lo + i + g];
+      ginc = tot;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int nb = __shfl_up_sync(0xffffffffu, ginc, o);
-      if (lane >= o) ginc += nb;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, ginc, o);
+        if (lane >= o) ginc += nb;
+      }
+      if (lane == 31) gws[w] = ginc;
     }
-    if (lane == 31) gws[w] = ginc;
     bar();
-    int grun = ginc - tot;
-    if (NW <= 4) {
-#pragma unroll
-      for (int k = 0; k < NW; ++k) if (k < w) grun += gws[k];
-    } else {
-      const int wt = lane < NW ? gws[lane] : 0;
+    if (g < VT) {
+      int grun = ginc - tot;
+      const int wt = lane < (VT >> 5) ? gws[lane] : 0;
       int winc = wt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -189,10 +180,10 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
         if (lane >= o) winc += nb;
       }
       grun += __shfl_sync(0xffffffffu, winc - wt, w);
-    }
 #pragma unroll 4
-    for (int i = 0; i < gl; ++i) { grun += sG[g_lo + i + g]; sG[g_lo + i + g] = grun; }
-    if (g == 0) sG[K + (K >> gsh)] = N;                    // G[K]: every C[j] <= B_K
+      for (int i = 0; i < gl; ++i) { grun += sG[g_lo + i + g]; sG[g_lo + i + g] = grun; }
+      if (g == 0) sG[K + (K >> gsh)] = N;                  // G[K]: every C[j] <= B_K
+    }
     bar();
   }
 
@@ -259,12 +250,16 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (n0 + k < N) a.anc[bt * N + n0 + k] = anc[k];
     }
+    if (sAnc != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (n0 + k < N) sAnc[n0 + k] = anc[k];
+    }
   }
 }
 
 // the 128-thread compute-group form used inside the persistent tensor-core filter kernel
 __device__ __forceinline__ void resample_group(const ResampleArgs& a, int b, int t, unsigned char* region, int g, int bar_id) {
-  resample_lean<kRgThreads, true>(a, b, t, region, g, RgGroupBar{bar_id});
+  resample_lean<true>(a, b, t, region, g, kRgThreads, RgGroupBar{bar_id});
 }
 
 }  // namespace psvo

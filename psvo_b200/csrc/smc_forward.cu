@@ -46,7 +46,8 @@ struct StepConsts {        // per-CTA constants in shared memory
   float sf[DXP];           // stddev used by f_lp
   float sp[DXP];           // proposal stddev (fused or s1)
   float inv1[DXP], inv2[DXP];
-  float sg[PSVO_MAX_DY];
+  float inv_sp[DXP], inv_sf[DXP];   // reciprocals: the standardised residuals are multiplications in the particle loop
+  float sg[PSVO_MAX_DY], inv_sg[PSVO_MAX_DY];
   float ld_p, ld_f, ld_g;  // sum log stddev
 };
 
@@ -64,9 +65,10 @@ __device__ __forceinline__ void step_consts_init(const PropArgs& a, bool t0, Ste
     const float sfd = f_is_d1 ? s1 : a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
     const float i1 = 1.0f / s1, i2 = 1.0f / s2;
     C->s1[d] = s1; C->sf[d] = sfd; C->inv1[d] = i1; C->inv2[d] = i2;
-    C->sp[d] = two_q ? 1.0f / (i1 + i2) : s1;
+    const float spv = two_q ? 1.0f / (i1 + i2) : s1;
+    C->sp[d] = spv; C->inv_sp[d] = 1.0f / spv; C->inv_sf[d] = 1.0f / sfd;
   }
-  for (int i = threadIdx.x; i < PSVO_MAX_DY; i += blockDim.x) C->sg[i] = a.sig[SIG_G * 32 + i];
+  for (int i = threadIdx.x; i < PSVO_MAX_DY; i += blockDim.x) { const float v = a.sig[SIG_G * 32 + i]; C->sg[i] = v; C->inv_sg[i] = 1.0f / v; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float lp = 0.f, lf = 0.f, lg = 0.f;
@@ -173,8 +175,8 @@ __device__ __forceinline__ void propagate_tile(const PropArgs& a, const StepCons
           m = C->sp[d] * (C->inv1[d] * mu1[pp][d] + C->inv2[d] * m2);
         }
         const float X = m + C->sp[d] * e[d];
-        const float zq = (X - m) / C->sp[d];
-        const float zf = (X - muf[pp][d]) / C->sf[d];
+        const float zq = (X - m) * C->inv_sp[d];
+        const float zf = (X - muf[pp][d]) * C->inv_sf[d];
         if (d < Dx) { qs = fmaf(zq, zq, qs); fsum = fmaf(zf, zf, fsum); }
         x[pp][d] = d < Dx ? X : 0.0f;
       }
@@ -206,7 +208,7 @@ __device__ __forceinline__ void propagate_tile(const PropArgs& a, const StepCons
           const float y = a.obs[bt * Dy + d];
           float z;
           if (poisson) z = y - (softplus(mug[pp][d]) + 1e-6f);
-          else z = (y - mug[pp][d]) / C->sg[d];
+          else z = (y - mug[pp][d]) * C->inv_sg[d];
           gsum = fmaf(z, z, gsum);
         }
       }
@@ -282,7 +284,7 @@ PropPlan plan_propagate(const PropArgs& a) {
     for (int k = 1; k < net.n_hidden; ++k) n += round4(net.width[k - 1] * net.width[k]) + round4(net.width[k]);
     return n + (size_t)net.width[net.n_hidden - 1] * dout_pad + dout_pad;
   };
-  fl += 128;   // StepConsts upper bound (floats)
+  fl += 192;   // StepConsts upper bound (floats)
   fl += add(DXP, DXP, a.q1);
   if (sep_f) fl += add(DXP, DXP, a.f);
   fl += add(DXP, DYP, a.g);
@@ -333,6 +335,9 @@ int launch_propagate(PropArgs a, const PropPlan& pl, cudaStream_t st) {
 // uniform's 24-bit range (B_k = draw_threshold(total, k 2^24/K)).  A child whose uniform falls in slice k has its ancestor in
 // [G[k], G[k+1]] -- about one particle wide -- so the inverse-CDF search is 1-2 probes of the CDF instead of log2 N
 // bank-conflicting ones; the result is the same upper bound, bit for bit.
+template <bool NC>
+__device__ __forceinline__ void gather_children(const ResampleArgs& a, size_t bt, const int* sAnc, int n_lo, int n_hi, int tid, int nt);
+
 template <bool NC>
 __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int part, int nparts, int t, unsigned char* smraw,
                                               unsigned long long* sscr, float* fscr, int* sG = nullptr, int kbits = 0) {
@@ -523,7 +528,14 @@ __device__ __forceinline__ void resample_body(const ResampleArgs& a, int b, int 
   __syncthreads();
 
   if (a.skip_gather) return;                     // the propagate launch of t+1 gathers (PropArgs::anc_prev)
-  // ancestor gather X_anc[t][n] = X_t[anc[n]]: consecutive threads write consecutive 16-byte pieces of the children
+  gather_children<NC>(a, bt, sAnc, n_lo, n_hi, tid, nt);
+}
+
+// ancestor gather X_anc[t][n] = X_t[anc[n]] for the children [n_lo, n_hi) (sAnc[n - n_lo] = ancestor of child n): consecutive
+// threads write consecutive 16-byte pieces of the children
+template <bool NC>
+__device__ __forceinline__ void gather_children(const ResampleArgs& a, size_t bt, const int* sAnc, int n_lo, int n_hi, int tid, int nt) {
+  const int N = a.N, Dx = a.Dx;
   const float* Xt = a.Xs + bt * N * Dx;
   float* Xa = a.X_anc + bt * N * Dx;
   const int nchild = n_hi - n_lo;
@@ -579,7 +591,7 @@ __global__ void __launch_bounds__(1024) smc_resample_lean_kernel(ResampleArgs a)
   griddep_launch_dependents();               // the next propagate launch may stage its weights while this kernel runs
   griddep_wait();                            // log_W_t / X_t of the propagate launch before this one
   const int b = blockIdx.x, t = a.t, N = a.N, Dx = a.Dx;
-  resample_lean<1024, false>(a, b, t, smraw, threadIdx.x, RgBlockBar{});
+  resample_lean<false>(a, b, t, smraw, threadIdx.x, 1024, RgBlockBar{});
   if (a.skip_gather) return;
   __syncthreads();                           // this block's ancestor indices are in global memory: read them back through L2
   const size_t bt = (size_t)b * a.T + t;
@@ -614,6 +626,8 @@ __global__ void __launch_bounds__(1024) smc_resample_lean_kernel(ResampleArgs a)
 // N = 1024: the per-step critical path is then a handful of barriers)
 __host__ __device__ constexpr int persist_max_block(int DXP, int DYP) { return (DXP <= 8 && DYP <= 8) ? 1024 : 256; }
 
+constexpr int kPersistLeanMinN = 512;
+
 template <int DXP, int DYP>
 __global__ void __launch_bounds__(persist_max_block(DXP, DYP), 1) smc_filter_persistent_kernel(PropArgs pa, ResampleArgs ra, int prop_floats) {
   extern __shared__ __align__(16) float smem[];
@@ -633,6 +647,7 @@ __global__ void __launch_bounds__(persist_max_block(DXP, DYP), 1) smc_filter_per
   p = mlp_stage<DXP, DYP>(pa.g, p, gs);
   float* scratch = p;
   unsigned char* rs_smem = reinterpret_cast<unsigned char*>(smem + prop_floats);
+  int* sAnc = reinterpret_cast<int*>(rs_smem + ((rg_smem_bytes(N, blockDim.x) + 15) & ~(size_t)15));
   step_consts_init<DXP>(pa, true, C0);
   step_consts_init<DXP>(pa, false, C1);
 
@@ -642,10 +657,24 @@ __global__ void __launch_bounds__(persist_max_block(DXP, DYP), 1) smc_filter_per
       const StepConsts<DXP>* C = t == 0 ? C0 : C1;
       for (int n0 = 0; n0 < N; n0 += tile) propagate_tile<DXP, DYP, 1>(pa, C, q1s, fs, gs, scratch, b, n0, t);
       __syncthreads();                     // log_W_t / X_t of this sequence written (block-scope visibility)
-      resample_body<false>(ra, b, 0, 1, t, rs_smem, sscr, fscr);
+      if (N >= kPersistLeanMinN) {
+        // thread-contiguous resampling (resample_group.cuh): guide table, one shuffle scan per warp, same indices bit for bit
+        resample_lean<false>(ra, b, t, rs_smem, threadIdx.x, blockDim.x, RgBlockBar{}, sAnc);
+        __syncthreads();
+        if (!ra.skip_gather) gather_children<false>(ra, (size_t)b * ra.T + t, sAnc, 0, N, threadIdx.x, blockDim.x);
+      } else {
+        resample_body<false>(ra, b, 0, 1, t, rs_smem, sscr, fscr);      // few particles: the plain search is a shorter chain than the guide table's phases
+      }
       __syncthreads();                     // X_anc_t / logWbar written
     }
   }
+}
+
+// resampling region of the persistent kernel: resample_lean's arrays + the ancestors for the gather (N >= kPersistLeanMinN), or
+// resample_body's CDF | log weights | ancestors
+static size_t persist_resample_bytes(int N, int block) {
+  if (N < kPersistLeanMinN) return (size_t)N * 16;
+  return ((rg_smem_bytes(N, block) + 15) & ~(size_t)15) + (size_t)N * sizeof(int);
 }
 
 static bool persistent_env() {
@@ -683,10 +712,10 @@ bool persistent_filter_supported(const PropArgs& a, const PropPlan& pl, size_t* 
     for (int k = 1; k < net.n_hidden; ++k) n += round4(net.width[k - 1] * net.width[k]) + round4(net.width[k]);
     return n + (size_t)net.width[net.n_hidden - 1] * dout_pad + dout_pad;
   };
-  size_t fl = 256 + add(DXP, DXP, a.q1) + (sep_f ? add(DXP, DXP, a.f) : 0) + add(DXP, DYP, a.g);
+  size_t fl = 384 + add(DXP, DXP, a.q1) + (sep_f ? add(DXP, DXP, a.f) : 0) + add(DXP, DYP, a.g);
   if (pl.scratch_half > 0) fl += 2 * (size_t)(pl.scratch_half / (pl.block * pl.ppt)) * block;
   fl = (fl + 3) & ~(size_t)3;
-  const size_t total = fl * sizeof(float) + (size_t)a.N * 16;
+  const size_t total = fl * sizeof(float) + persist_resample_bytes(a.N, block);
   if (total > 100 * 1024) return false;
   *smem_out = total; *block_out = block;
   return true;
@@ -695,7 +724,7 @@ bool persistent_filter_supported(const PropArgs& a, const PropPlan& pl, size_t* 
 int launch_filter_persistent(PropArgs pa, const ResampleArgs& ra, const PropPlan& pl, cudaStream_t st) {
   size_t smem = 0; int block = 0;
   PSVO_REQUIRE(persistent_filter_supported(pa, pl, &smem, &block), "persistent filter kernel does not support this shape");
-  const int prop_floats = (int)((smem - (size_t)pa.N * 16) / sizeof(float));
+  const int prop_floats = (int)((smem - persist_resample_bytes(pa.N, block)) / sizeof(float));
   pa.scratch_half = pl.scratch_half > 0 ? (pl.scratch_half / (pl.block * pl.ppt)) * block : 0;
   const int DXP = pad_dx(pa.Dx), DYP = pad_dy(pa.Dy);
   const int grid = pa.B;
