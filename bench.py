@@ -280,7 +280,8 @@ def run_ours(args, w, rank, world, local_rank):
     path = int(lib.psvo_smc_forward_path(C.byref(Fn.make_dims(N, B, T, Dx, w["Dy"], w["Dy"], w["Dy"], flags)),
                                          C.byref(Fn.params_struct(P, []))))
     kernel_name = {0: "smc_propagate_kernel (FP32, per step)", 1: "smc_filter_persistent_kernel (one launch per pass)",
-                   2: "smc_propagate_tc_kernel<32> (tcgen05, per step)"}.get(path, "?")
+                   2: "smc_propagate_tc_kernel<32> (tcgen05, per step)",
+                   3: "smc_filter_tc_persistent_kernel<32> (tcgen05, one launch per pass, resampling inside; opt-in PSVO_TC_PERSIST=1)"}.get(path, "?")
     roof.update({"kernel": kernel_name, "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
                  "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
                  "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,
@@ -288,13 +289,13 @@ def run_ours(args, w, rank, world, local_rank):
                                           "mlp_rows": kms[2] / max(sum(kms), 1e-9)},
                  "hbm_frac_whole_step": (bytes_ps * B * N * T / (step_ms * 1e-3) / 1e9) / peaks["hbm_gbs"]})
     H = w["H"]
-    if path == 2:
+    if path in (2, 3):
         # tensor-core propagate kernel: what the tcgen05 pipe is actually busy with.  Every MMA of the pipeline is in TS form
         # (A operand in tensor memory) and occupies the pipe for N/2 cycles (+ ~1; profiles/microbench/r2_pipe_bench.cu): per
         # 16-unit stage layer 1 is 4 MMAs of N = 16, layer 2 is 3 MMAs of N = 16 (q1) or N = 32 (g).
         nst = H[0] // 16
         cyc = 2 * nst * 4 * 9 + nst * 3 * 9 + nst * 3 * 17
-        tiles_per_sm = B * ((N + 127) // 128) / 148.0
+        tiles_per_sm = B * ((N + 127) // 128) * steps_per_launch / 148.0
         roof["tensor_pipe"] = {"pipe_cycles_per_tile": cyc, "occupancy": tiles_per_sm * cyc / (prop_ms_avg * 1e-3 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6),
                                "note": "instruction-time occupancy of the tcgen05 pipe (TS-form M128 K16 MMAs: N/2 + 1 cycles each); frac above "
                                        "counts algorithmic fp32 FLOP against the dense bf16 peak although the 1e-5 bar needs a 3-term fp16 split"}

@@ -102,5 +102,5 @@ class PSVO(SVO):
         T, N, B = f_log_probs.shape
         joint = (f_log_probs + g_log_probs).sum(0)
         prop = bw_log_Omegas.sum(0)
-        lse = Fn.logsumexp((joint - prop).t().contiguous())
+        lse = Fn.logsumexp_ad((joint - prop).t().contiguous())
         return (lse - torch.log(torch.tensor(float(N), device=lse.device))).mean()

@@ -13,5 +13,5 @@ class PSVOwR(PSVO):
     def compute_log_ZSMC(bw_log_W):
         """PSVOwR.py:52-63 on a (time, n_particles, batch_size) tensor."""
         T, N, B = bw_log_W.shape
-        lse = Fn.logsumexp(bw_log_W.permute(0, 2, 1).contiguous())
+        lse = Fn.logsumexp_ad(bw_log_W.permute(0, 2, 1).contiguous())
         return (lse - torch.log(torch.tensor(float(N), device=lse.device))).sum(0).mean()

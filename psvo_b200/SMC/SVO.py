@@ -145,15 +145,15 @@ class SVO:
         return pre_X0, pre_obs
 
     def sample_from_2_dist(self, dist1, dist2, d1_input, d2_input, sample_size=()):
-        """Diagonal branch of SVO.py:182-197,228-232 as a stand-alone (non-fused, non-differentiable) helper."""
+        """Diagonal branch of SVO.py:182-197,228-232 as a stand-alone (non-fused) helper; differentiable like the original."""
         d1, d2 = dist1.get_mvn(d1_input), dist2.get_mvn(d2_input)
         i1, i2 = 1.0 / d1.scale_diag, 1.0 / d2.scale_diag
         cov = 1.0 / (i1 + i2)
         mean = cov * (i1 * d1.loc + i2 * d2.loc)
         ss = () if sample_size == () else (sample_size,)
         X = mean + cov * torch.randn(ss + tuple(mean.shape), device=mean.device)
-        q_lp = Fn.mvn_log_prob(X.detach(), mean.detach().expand_as(X), cov.detach())
-        f_lp = Fn.mvn_log_prob(X.detach(), d1.loc.detach().expand_as(X), d1.scale_diag.detach())
+        q_lp = Fn.mvn_log_prob_ad(X, mean.expand_as(X), cov)
+        f_lp = Fn.mvn_log_prob_ad(X, d1.loc.expand_as(X), d1.scale_diag)
         return X, q_lp, f_lp
 
     def get_resample_idx(self, log_W, sample_size=(), uniforms=None):
@@ -191,7 +191,7 @@ class SVO:
     def compute_log_ZSMC(log_Ws):
         """SVO.py:302-311: log_Ws (time, n_particles, batch_size) -> scalar."""
         T, N, B = log_Ws.shape
-        lse = Fn.logsumexp(log_Ws.permute(0, 2, 1).contiguous())               # (T,B)
+        lse = Fn.logsumexp_ad(log_Ws.permute(0, 2, 1).contiguous())            # (T,B)
         return lse.sum(0).mean()
 
     def n_step_prediction(self, n_steps, hidden, obs):

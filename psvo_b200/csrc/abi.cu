@@ -1,7 +1,9 @@
 // abi.cu -- extern "C" entry points of include/psvo.h for the forward filter, plus error plumbing.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 #include "smc_kernels.h"
 
@@ -23,13 +25,30 @@ int fail(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static int cache[64] = {0};                   // per device: one process may drive several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
-  return n;
+  return cache[dev];
+}
+
+int ensure_dyn_smem(const void* kernel, size_t bytes) {
+  if (bytes <= 40 * 1024) return 0;             // within the default limit
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> have;
+  int dev = 0;
+  PSVO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& h = have[std::make_pair(dev, kernel)];
+  if (bytes > h) {
+    PSVO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    h = bytes;
+  }
+  return 0;
 }
 
 // ---- measurement hooks

@@ -61,11 +61,7 @@ static int launch_particle_mlp(const psvo_mlp& net, const float* in, long long s
   PSVO_REQUIRE(net.n_hidden <= 1, "psvo_ffbsi: per-particle networks with more than one hidden layer are not supported yet");
   const size_t smem = staged_bytes(net, DXP, DXP);
   auto kern = particle_mlp_kernel<DXP, DXP>;
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(kern, smem);
   const long long rows = (long long)B * N;
   const int block = rows >= 128 ? 128 : 32;
   long long grid = (rows + block - 1) / block;
@@ -367,11 +363,7 @@ __global__ void __launch_bounds__(256) ffbsi_logz_kernel(const float* __restrict
 template <int DXP, int DYP>
 static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
   auto kern = ffbsi_step_kernel<DXP, DYP>;
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(kern, smem);
   ProfScope ps_(PK_FFBSI, st);
   PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();

@@ -613,17 +613,7 @@ static size_t staged_fl(const psvo_mlp& net, int din_pad, int dout_pad) {
 
 template <typename K>
 static int launch_fb(K kern, const FbArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-  if (smem > 40 * 1024) {
-    // raise the dynamic shared-memory limit once per kernel (a driver call per launch would dominate small steps)
-    static std::mutex mu;
-    static std::map<const void*, size_t> configured;
-    std::lock_guard<std::mutex> lk(mu);
-    size_t& have = configured[reinterpret_cast<const void*>(kern)];
-    if (smem > have) {
-      PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      have = smem;
-    }
-  }
+  PSVO_DYN_SMEM(kern, smem);      // once per (device, kernel): a driver call per launch would dominate small steps
   ProfScope ps_(PK_FFBSI, st);
   PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();

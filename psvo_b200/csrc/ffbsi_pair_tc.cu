@@ -346,8 +346,7 @@ int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
   }
   const PtSmem L = pt_layout();
   const size_t smem = L.total + 128;
-  static bool cfg = false;
-  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(ffbsi_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+  PSVO_DYN_SMEM(ffbsi_pair_tc_kernel, smem);
   const long long ncand = (long long)a.N * a.M;
   const long long work = (long long)a.B * (((ncand + 127) / 128 + kPtGroups - 1) / kPtGroups);
   const int grid = (int)(work < num_sms() ? work : num_sms());

@@ -421,8 +421,7 @@ int launch_mlp_bwd_tc(const psvo_mlp& net, const unsigned char* image, const flo
   a.B = B; a.N = N; a.H = net.width[0]; a.NP = NP; a.d_in = net.d_in; a.d_out = net.d_out;
   const long long tiles = (rows + 127) / 128;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  static bool cfg = false;
-  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+  PSVO_DYN_SMEM(mlp_bwd_tc_kernel, 227 * 1024);
   ProfScope ps_(PK_BWD, st);
   mlp_bwd_tc_kernel<<<grid, 352, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();

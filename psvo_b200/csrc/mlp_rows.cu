@@ -71,11 +71,7 @@ int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, f
   const MlpShape s = shape_of(net);
   const size_t smem = 2 * (size_t)kRowTile * s.maxw * sizeof(float);
   PSVO_REQUIRE(smem <= 200 * 1024, "MLP layer width %d too large", s.maxw);
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(mlp_rows_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(mlp_rows_forward_kernel, smem);
   const int64_t tiles = (rows + kRowTile - 1) / kRowTile;
   const int grid = (int)(tiles < 4 * (int64_t)num_sms() ? tiles : 4 * (int64_t)num_sms());
   ProfScope ps_(PK_ROWS, st);
@@ -190,11 +186,7 @@ int launch_mlp_rows_backward(const psvo_mlp& net, const float* x, const float* g
   const MlpShape s = shape_of(net);
   const size_t smem = ((size_t)kRowTile * (s.sum_in + 2 * s.maxw) + s.n_param) * sizeof(float);
   PSVO_REQUIRE(smem <= 220 * 1024, "MLP too large for the row-backward kernel (%zu B shared memory)", smem);
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(mlp_rows_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(mlp_rows_backward_kernel, smem);
   psvo_mlp_grad gr;
   if (grads != nullptr) gr = *grads;
   else for (int k = 0; k <= PSVO_MAX_HIDDEN; ++k) { gr.W[k] = nullptr; gr.b[k] = nullptr; }

@@ -122,11 +122,7 @@ PSVO_API int psvo_resample(const float* logits, const float* u, int64_t rows, in
   if (rows == 0 || n == 0) return 0;
   const size_t smem = (size_t)K * (sizeof(unsigned long long) + sizeof(float));
   PSVO_REQUIRE(smem <= 200 * 1024, "psvo_resample: K=%d too large for the shared-memory CDF", K);
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(resample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(resample_rows_kernel, smem);
   const int work = K > n ? K : n;
   const int block = work >= 4096 ? 512 : (work >= 1024 ? 256 : (work >= 256 ? 128 : (work > 32 ? 64 : 32)));
   PSVO_REQUIRE(rows <= 0x7fffffffLL, "psvo_resample: too many rows");

@@ -27,6 +27,10 @@ inline int pad_dx(int d) { return d <= 4 ? 4 : (d <= 8 ? 8 : 16); }
 inline int pad_dy(int d) { return d <= 4 ? 4 : (d <= 8 ? 8 : (d <= 16 ? 16 : 32)); }
 
 int num_sms();
+// Raise a kernel's dynamic shared-memory limit; remembered per (device, kernel) because the attribute is per device: one process
+// may drive several GPUs.  Returns 0 or the cudaError_t (with psvo_last_error() set).
+int ensure_dyn_smem(const void* kernel, size_t bytes);
+#define PSVO_DYN_SMEM(kern, bytes) do { if (int e_ = ::psvo::ensure_dyn_smem(reinterpret_cast<const void*>(kern), (size_t)(bytes))) return e_; } while (0)
 
 // ---- measurement hooks (include/psvo.h: psvo_profile_*) ------------------------------------------------
 enum { PK_PROP = 0, PK_RESAMPLE, PK_ROWS, PK_SIGMA, PK_BWD, PK_FFBSI, PK_OPS, PK_SPARE };

@@ -477,11 +477,7 @@ __global__ void sigma_grad_kernel(SigmaGradArgs a) {
 template <int DXP, int DYP>
 static int launch_emission_t(const BwdArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
   auto kern = bwd_emission_kernel<DXP, DYP>;
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(kern, smem);
   ProfScope ps_(PK_BWD, st);
   PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();
@@ -490,11 +486,7 @@ static int launch_emission_t(const BwdArgs& a, int block, int grid, size_t smem,
 template <int DXP>
 static int launch_proposal_t(const BwdArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
   auto kern = bwd_proposal_kernel<DXP>;
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(kern, smem);
   ProfScope ps_(PK_BWD, st);
   PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, pdl_enabled(), a));
   PSVO_LAUNCH_CHECK();

@@ -255,11 +255,7 @@ __global__ void __launch_bounds__(256) smc_propagate_kernel(PropArgs a) {
 template <int DXP, int DYP, int PPT>
 static int launch_propagate_t(const PropArgs& a, int block, int grid, size_t smem, cudaStream_t st) {
   auto kern = smc_propagate_kernel<DXP, DYP, PPT>;
-  static size_t configured = 0;          // per instantiation
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(kern, smem);
   ProfScope ps_(PK_PROP, st);
   PSVO_CUDA(launch_pdl(kern, dim3(grid), dim3(block), smem, st, a.pdl != 0, a));
   PSVO_LAUNCH_CHECK();
@@ -732,7 +728,7 @@ int launch_filter_persistent(PropArgs pa, const ResampleArgs& ra, const PropPlan
 #define PSVO_CASE_P(X, Y)                                                                                           \
   if (DXP == X && DYP == Y) {                                                                                       \
     auto kern = smc_filter_persistent_kernel<X, Y>;                                                                 \
-    if (smem > 40 * 1024) PSVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    PSVO_DYN_SMEM(kern, smem);                                                                                      \
     kern<<<grid, block, smem, st>>>(pa, ra, prop_floats);                                                           \
     PSVO_LAUNCH_CHECK();                                                                                            \
     return 0;                                                                                                       \
@@ -761,11 +757,7 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
     static const bool lean_off = getenv("PSVO_RESAMPLE_LEAN") != nullptr && getenv("PSVO_RESAMPLE_LEAN")[0] == '0';
     const size_t lsm = rg_smem_bytes(N, 1024);
     if (!lean_off && parts == 1 && N >= 2048 && lsm <= 220 * 1024) {
-      static size_t lean_configured = 0;
-      if (lsm > 40 * 1024 && lsm > lean_configured) {
-        PSVO_CUDA(cudaFuncSetAttribute(smc_resample_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-        lean_configured = lsm;
-      }
+      PSVO_DYN_SMEM(smc_resample_lean_kernel, lsm);
       ProfScope ps_(PK_RESAMPLE, st);
       PSVO_CUDA(launch_pdl(smc_resample_lean_kernel, dim3(a.B), dim3(1024), lsm, st, a.pdl != 0, a));
       PSVO_LAUNCH_CHECK();
@@ -784,11 +776,7 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
     guide_off = (int)((smem + 15) & ~(size_t)15);
     smem = (size_t)guide_off + ((size_t)(1 << kbits) + 1) * sizeof(int);
   }
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    PSVO_CUDA(cudaFuncSetAttribute(smc_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  PSVO_DYN_SMEM(smc_resample_kernel, smem);
   ProfScope ps_(PK_RESAMPLE, st);
   PSVO_CUDA(launch_pdl(smc_resample_kernel, dim3(a.B, parts), dim3(block), smem, st, a.pdl != 0, a, guide_off, kbits));
   PSVO_LAUNCH_CHECK();

@@ -1027,8 +1027,7 @@ int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st) {
   const long long tiles = ((long long)a.B * a.N + 127) / 128;
   long long grid = (tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
-  static bool cfg = false;
-  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(tc_fwd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+  PSVO_DYN_SMEM(tc_fwd2_kernel<32>, 227 * 1024);
   ProfScope ps_(PK_BWD, st);
   tc_fwd2_kernel<32><<<(int)grid, kTcThreads, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
@@ -1060,8 +1059,7 @@ int launch_ffbsi_cand_tc(const CandTcArgs& a, cudaStream_t st) {
   const long long tiles = (long long)a.B * (((long long)a.N * a.M + 127) / 128);
   long long grid = (tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
-  static bool cfg = false;
-  if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(ffbsi_cand_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+  PSVO_DYN_SMEM(ffbsi_cand_tc_kernel<32>, 227 * 1024);
   ProfScope ps_(PK_FFBSI, st);
   ffbsi_cand_tc_kernel<32><<<(int)grid, kTcThreads, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
@@ -1106,13 +1104,13 @@ int launch_propagate_tc(const PropArgs& a, cudaStream_t st) {
   if (grid > num_sms()) grid = num_sms();
   ProfScope ps_(PK_PROP, st);
   {
-    static bool cfg = false;      // (the trace build carries 8 B of static shared memory)
+    // (the trace build carries 8 B of static shared memory)
 #ifdef PSVO_TC_TRACE
     const int max_dyn = 227 * 1024 - 1024;
 #else
     const int max_dyn = 227 * 1024;
 #endif
-    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(smc_propagate_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)); cfg = true; }
+    PSVO_DYN_SMEM(smc_propagate_tc_kernel<32>, max_dyn);
     PSVO_CUDA(launch_pdl(smc_propagate_tc_kernel<32>, dim3(grid), dim3(kTcThreads), smem, st, a.pdl != 0, a));
   }
   PSVO_LAUNCH_CHECK();
@@ -1154,7 +1152,7 @@ int launch_filter_tc_persistent(PropArgs a, const ResampleArgs& ra, int* sync, c
   a.t = 0; a.anc_prev = ra.anc; a.logWbar = nullptr;
   PSVO_CUDA(cudaMemsetAsync(sync, 0, tc_filter_sync_bytes(a.B), st));
   ProfScope ps_(PK_PROP, st);
-  PSVO_CUDA(cudaFuncSetAttribute(smc_filter_tc_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  PSVO_DYN_SMEM(smc_filter_tc_persistent_kernel<32>, 227 * 1024);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -172,12 +172,10 @@ int launch_particle_mlp_tc(const psvo_mlp& net, const float* in, long long seq_s
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   ProfScope ps_(PK_ROWS, st);
   if (NP == 16) {
-    static bool cfg = false;
-    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(particle_mlp_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    PSVO_DYN_SMEM(particle_mlp_tc_kernel<16>, 227 * 1024);
     particle_mlp_tc_kernel<16><<<grid, 128, smem, st>>>(net, in, seq_stride, B, N, out);
   } else {
-    static bool cfg = false;
-    if (!cfg) { PSVO_CUDA(cudaFuncSetAttribute(particle_mlp_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    PSVO_DYN_SMEM(particle_mlp_tc_kernel<32>, 227 * 1024);
     particle_mlp_tc_kernel<32><<<grid, 128, smem, st>>>(net, in, seq_stride, B, N, out);
   }
   PSVO_LAUNCH_CHECK();

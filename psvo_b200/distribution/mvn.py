@@ -47,11 +47,11 @@ class tf_mvn(torch.nn.Module, distribution):
         ss = () if sample_shape == () else ((sample_shape,) if isinstance(sample_shape, int) else tuple(sample_shape))
         eps = torch.randn(ss + tuple(mvn.loc.shape), device=mvn.loc.device)
         sample = mvn.loc + mvn.scale_diag * eps
-        return sample, Fn.mvn_log_prob(sample.detach(), mvn.loc.detach(), mvn.scale_diag.detach())
+        return sample, Fn.mvn_log_prob_ad(sample, mvn.loc, mvn.scale_diag)
 
     def log_prob(self, Input, output, name=None):
         mvn = self.get_mvn(Input)
-        return Fn.mvn_log_prob(output.detach(), mvn.loc.detach(), mvn.scale_diag.detach())
+        return Fn.mvn_log_prob_ad(output, mvn.loc, mvn.scale_diag)
 
     def mean(self, Input, name=None):
         return self.get_mvn(Input).loc

@@ -20,7 +20,7 @@ class tf_poisson(torch.nn.Module, distribution):
 
     def log_prob(self, Input, output, name=None):
         p = self.get_poisson(Input)
-        return Fn.mvn_log_prob(output.detach(), p.loc.detach(), None)
+        return Fn.mvn_log_prob_ad(output, p.loc, None)
 
     def mean(self, Input, name=None):
         return self.get_poisson(Input).loc

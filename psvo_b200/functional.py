@@ -403,6 +403,65 @@ def logsumexp(x):
     return out
 
 
+def _unbroadcast(g, shape):
+    """sum a gradient of a broadcast result back to the operand's shape"""
+    if g is None:
+        return None
+    while g.dim() > len(shape):
+        g = g.sum(0)
+    for i, n in enumerate(shape):
+        if n == 1 and g.shape[i] != 1:
+            g = g.sum(i, keepdim=True)
+    return g
+
+
+class _MvnLogProbFn(torch.autograd.Function):
+    """psvo_mvn_log_prob with its closed-form reverse mode, so that the stand-alone helpers of the facade (tf_mvn.log_prob,
+    sample_and_log_prob, tf_poisson.log_prob, SVO.sample_from_2_dist) stay differentiable like their TF originals"""
+
+    @staticmethod
+    def forward(ctx, x, mu, sigma):
+        ctx.save_for_backward(x, mu, sigma if sigma is not None else torch.empty(0, device=x.device))
+        ctx.has_sigma = sigma is not None
+        return mvn_log_prob(x.detach(), mu.detach(), None if sigma is None else sigma.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mu, sigma = ctx.saved_tensors
+        inv = 1.0 / sigma if ctx.has_sigma else torch.ones(x.shape[-1], device=x.device)
+        z = (x - mu) * inv                                   # broadcast (..., D)
+        gz = g[..., None] * z
+        gx = _unbroadcast(-gz * inv, x.shape) if ctx.needs_input_grad[0] else None
+        gmu = _unbroadcast(gz * inv, mu.shape) if ctx.needs_input_grad[1] else None
+        gs = None
+        if ctx.has_sigma and ctx.needs_input_grad[2]:
+            gs = _unbroadcast(g[..., None] * (z * z - 1.0) * inv, sigma.shape)
+        return gx, gmu, gs
+
+
+def mvn_log_prob_ad(x, mu, sigma=None):
+    """differentiable MultivariateNormalDiag(mu, sigma).log_prob(x)"""
+    return _MvnLogProbFn.apply(x, mu, sigma)
+
+
+class _LogSumExpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        out = logsumexp(x.detach())
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        return g[..., None] * torch.exp(x - out[..., None])
+
+
+def logsumexp_ad(x):
+    """differentiable log-sum-exp over the last axis"""
+    return _LogSumExpFn.apply(x)
+
+
 def fill_normal(seed, stream_id, first_particle, particles, width, device):
     lib = L.load()
     out = torch.empty(particles, width, device=device, dtype=torch.float32)

@@ -1,0 +1,72 @@
+"""-m gpu: the resampling kernels behind the tensor-core forward filter.
+
+* the thread-contiguous kernel (smc_resample_lean_kernel, one 1024-thread CTA per sequence; taken when a launch has
+  enough sequences to give every SM one) against the order-independent rule of the oracle (SVO.get_resample_idx,
+  src/SMC/SVO.py:266-300): the kernel's own log-weight bits + the Philox uniforms -> identical ancestors, also for a
+  particle count that is neither a multiple of 4 nor of the 128-particle tile;
+* the opt-in persistent whole-filter kernel (PSVO_TC_PERSIST=1: resampling inside the kernel, per-sequence flags instead of
+  kernel boundaries) against the default per-step launches: every output bit-identical."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import psvo_oracle as O
+from gpu_util import to_dev, flags_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+Dx, Dy, H = 16, 32, [128]
+
+
+def _run(B, T, N, seed=5):
+    from psvo_b200 import functional as Fn
+    F = O.Flags()
+    P = O.make_params(3, Dx, Dy, Dy, Dy, H, F)
+    g = torch.Generator().manual_seed(17)
+    t = torch.arange(T, dtype=torch.float32)[None, :, None]
+    obs = torch.sin(0.3 * t + torch.rand(B, 1, Dy, generator=g) * 6.28) + 0.1 * torch.randn(B, T, Dy, generator=g)
+    fw = Fn.smc_forward_raw(to_dev(P, DEV), flags_of(F), obs.to(DEV), obs.to(DEV), obs[:, 0].contiguous().to(DEV), N, seed=seed)
+    return {k: fw[k] for k in ("Xs", "X_anc", "anc", "log_Ws", "lse", "logZ_b")}
+
+
+@pytest.mark.parametrize("N", [4096, 2501])
+def test_thread_contiguous_resampling_follows_the_rule(N):
+    from psvo_b200 import functional as Fn
+    B, T, seed = 80, 3, 5                                    # 80 sequences: one resampling CTA per sequence
+    r = _run(B, T, N, seed)
+    anc = r["anc"].long()
+    assert int(anc.min()) >= 0 and int(anc.max()) < N
+    assert torch.equal(r["X_anc"], torch.gather(r["Xs"], 2, anc[..., None].expand(B, T, N, Dx)))
+    lw = r["log_Ws"].cpu().numpy()
+    for (b, t) in [(0, 0), (1, 1), (41, 1), (B - 1, T - 1), (B - 1, 0)]:
+        u = Fn.fill_uniform(seed, 1, (b * T + t) * N, N, DEV).cpu().numpy()
+        want = O.resample_idx(lw[b, t][None], u[None])[0]
+        assert (anc[b, t].cpu().numpy() == want).all(), (b, t)
+    lse = torch.logsumexp(r["log_Ws"].double(), -1)
+    assert float((r["lse"].double() - lse).abs().max()) < 1e-4
+    assert float((r["logZ_b"].double() - lse.sum(1)).abs().max()) < 1e-3
+
+
+@pytest.mark.timeout(600)
+def test_persistent_tensor_core_filter_is_bit_identical(tmp_path):
+    if os.environ.get("PSVO_TC_PERSIST") == "1":
+        pytest.skip("inside the persistent re-run")
+    B, T, N = 80, 5, 4096
+    ref = _run(B, T, N)
+    dump = str(tmp_path / "persist.pt")
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_resample_paths as m; "
+            "import ctypes as C; from psvo_b200 import _lib; lib = _lib.load(); kl = (C.c_int64 * 8)(); lib.psvo_profile_read(None, kl); "
+            "r = m._run(%d, %d, %d); kl = (C.c_int64 * 8)(); lib.psvo_profile_read(None, kl); "
+            "d = {k: v.cpu() for k, v in r.items()}; d['propagate_launches'] = int(kl[0]); torch.save(d, %r)") % (
+                ROOT, os.path.join(ROOT, "tests"), B, T, N, dump)
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSVO_TC_PERSIST="1"), capture_output=True, text=True,
+                       cwd=ROOT, timeout=500)
+    assert p.returncode == 0, p.stderr[-3000:]
+    got = torch.load(dump)
+    assert got["propagate_launches"] == 1, got["propagate_launches"]       # the whole filter was ONE launch
+    for k in ("anc", "Xs", "X_anc", "log_Ws", "lse", "logZ_b"):
+        assert torch.equal(ref[k].cpu(), got[k]), k
