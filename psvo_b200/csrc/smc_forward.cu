@@ -754,9 +754,10 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st) {
   }
   {
     // big particle sets with one CTA per sequence: the thread-contiguous kernel (PSVO_RESAMPLE_LEAN=0 keeps the older one)
-    static const bool lean_off = getenv("PSVO_RESAMPLE_LEAN") != nullptr && getenv("PSVO_RESAMPLE_LEAN")[0] == '0';
+    // PSVO_RESAMPLE_LEAN=2: test hook -- every launch takes this kernel, one CTA per sequence, whatever N and B
+    static const int lean_mode = [] { const char* e = getenv("PSVO_RESAMPLE_LEAN"); return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }();
     const size_t lsm = rg_smem_bytes(N, 1024);
-    if (!lean_off && parts == 1 && N >= 2048 && lsm <= 220 * 1024) {
+    if (lsm <= 220 * 1024 && (lean_mode == 2 || (lean_mode == 1 && parts == 1 && N >= 2048))) {
       PSVO_DYN_SMEM(smc_resample_lean_kernel, lsm);
       ProfScope ps_(PK_RESAMPLE, st);
       PSVO_CUDA(launch_pdl(smc_resample_lean_kernel, dim3(a.B), dim3(1024), lsm, st, a.pdl != 0, a));

@@ -70,3 +70,19 @@ def test_persistent_tensor_core_filter_is_bit_identical(tmp_path):
     assert got["propagate_launches"] == 1, got["propagate_launches"]       # the whole filter was ONE launch
     for k in ("anc", "Xs", "X_anc", "log_Ws", "lse", "logZ_b"):
         assert torch.equal(ref[k].cpu(), got[k]), k
+
+
+@pytest.mark.timeout(900)
+def test_forced_thread_contiguous_kernel_on_golden_and_oracle_cases():
+    """PSVO_RESAMPLE_LEAN=2 (test hook) sends EVERY per-step resampling launch through smc_resample_lean_kernel -- particle counts
+    from 1 to 4096, ragged N, IWAE (no resampling: log Wbar output), forced ancestors, reference-drawn uniforms -- and
+    PSVO_PERSISTENT=0 keeps the small shapes on the per-step path.  The reference-generated golden vectors (free-running
+    ancestors must equal the ones the reference drew) and the seeded oracle configurations must pass unchanged."""
+    if os.environ.get("PSVO_RESAMPLE_LEAN") == "2":
+        pytest.skip("already inside the forced re-run")
+    env = dict(os.environ, PSVO_RESAMPLE_LEAN="2", PSVO_PERSISTENT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_forward.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "golden_teacher_forced or golden_free_running or vs_oracle or philox_mode or systematic or sharded_equals"],
+                       env=env, capture_output=True, text=True, cwd=ROOT, timeout=850)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1500:]
