@@ -429,12 +429,17 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
   if (tid < DXP) sf[tid] = a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + tid];
   __syncthreads();
 
-  const int tiles_per_seq = (N + P - 1) / P;
+  // few particles (2 N <= P): the block splits the candidate loop of every particle j over S = P / NP2 slices (thread = (slice,
+  // j)), partial sums meet in shared memory in a fixed order, and the slice-0 threads carry on as the particles' owners
+  int NP2 = P, S = 1;
+  if (2 * N <= P) { NP2 = 1; while (NP2 < N) NP2 *= 2; S = P / NP2; }
+  const int slice = tid / NP2;
+  const int tiles_per_seq = S > 1 ? 1 : (N + P - 1) / P;
   const int work = a.B * tiles_per_seq;
   const long long ncand = (long long)N * M;
   for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
     const int b = wi / tiles_per_seq;
-    const int j = (wi - b * tiles_per_seq) * P + tid;
+    const int j = S > 1 ? tid % NP2 : (wi - b * tiles_per_seq) * P + tid;
     const bool live = j < N;
     const size_t btm = (size_t)b * T + (t - 1);
     float x[DXP], mus[DXP];
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
       for (int q = tid; q < nc * DXP; q += P) sCX[q] = cX[c0 * DXP + q];
       for (int q = tid; q < nc; q += P) { sCK[q] = cK[c0 + q]; sCP[q] = cP[c0 + q]; }
       __syncthreads();
-      for (int cc = 0; cc < nc; ++cc) {
+      for (int cc = slice; cc < nc; cc += S) {
         float dv[DXP];
         lds_vec<DXP>(sCX + cc * DXP, dv);
         float d2 = 0.f;
@@ -468,15 +473,33 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
         for (int d = 0; d < DXP; ++d) gm[d] = fmaf(w, dv[d], gm[d]);
       }
     }
+    if (S > 1) {
+      // partial sums of the slices -> the owner (slice 0), summed in slice order; the staging area is free until mlp_bwd_tile
+      __syncthreads();
+      float* part = stage + (size_t)tid * (2 + DXP);
+      part[0] = Gj; part[1] = Ksum;
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) part[2 + d] = gm[d];
+      __syncthreads();
+      if (slice == 0) {
+        for (int sl = 1; sl < S; ++sl) {
+          const float* q = stage + (size_t)(sl * NP2 + tid) * (2 + DXP);
+          Gj += q[0]; Ksum += q[1];
+#pragma unroll
+          for (int d = 0; d < DXP; ++d) gm[d] += q[2 + d];
+        }
+      }
+    }
+    const bool owner = live && slice == 0;
     float gmu[DXP], gx[DXP];
 #pragma unroll
-    for (int d = 0; d < DXP; ++d) gmu[d] = (live && d < Dx) ? gm[d] / sf[d] : 0.0f;
+    for (int d = 0; d < DXP; ++d) gmu[d] = (owner && d < Dx) ? gm[d] / sf[d] : 0.0f;
     // log Wbar[j] = log_W[j] - LSE_j log_W: the normaliser sends -softmax_j * sum_j' G_j' back, and sum_j' G_j' is
     // the sum of kappa over the candidates (sum_j rho = 1).  It vanishes for PSVO (sum_m (pi_m - delta) = 0), not for
     // PSVOwR (kappa = pi_m c).
-    if (live) a.g_log_Ws[btm * N + j] = Gj - expf(wb) * Ksum;
+    if (owner) a.g_log_Ws[btm * N + j] = Gj - expf(wb) * Ksum;
     mlp_bwd_tile<DXP, DXP>(fs, gfS, x, gmu, gx, stage);
-    if (live) {
+    if (owner) {
 #pragma unroll
       for (int d = 0; d < DXP; ++d) if (d < Dx) a.g_Xs[(btm * N + j) * Dx + d] = gx[d];
     }
@@ -750,6 +773,11 @@ PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p, const
   };
   int blockB, blockC; size_t smemB, smemC;
   if (int e = pick_block(DXP + 2 * staged_fl(a.f, DXP, DXP) + kBwdPairChunk * (DXP + 2), &blockB, &smemB)) return e;
+  if (N <= 64) {
+    // few particles: a 256-thread block whose extra threads split every particle's candidate loop (ffbsi_bwd_pair_kernel)
+    const size_t fl = DXP + 2 * staged_fl(a.f, DXP, DXP) + kBwdPairChunk * (DXP + 2) + (size_t)2 * kBwdChunk * (256 + 1) + (size_t)2 * 256 * DXP;
+    if (fl * sizeof(float) <= 220 * 1024) { blockB = 256; smemB = fl * sizeof(float); }
+  }
   if (int e = pick_block(2 * staged_fl(a.q1i, DXP, DXP), &blockC, &smemC)) return e;
   auto grid_of = [&](int block) {
     const int64_t work = (int64_t)B * ((N + block - 1) / block);
