@@ -492,6 +492,8 @@ def run_fwd_bwd(args, w, local_rank):
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     fwd_l, bwd_l = [], []
+    import gc
+    gc.collect(); gc.disable()                     # a generation-2 collection inside the reverse pass idles the device for ~0.1 s
     for i in range(args.steps):
         for p in model.parameters():
             p.grad = None
@@ -502,6 +504,7 @@ def run_fwd_bwd(args, w, local_rank):
         ev[2].record()
         torch.cuda.synchronize()
         fwd_l.append(ev[0].elapsed_time(ev[1])); bwd_l.append(ev[1].elapsed_time(ev[2]))
+    gc.enable()
     fwd_ms, bwd_ms = statistics.median(fwd_l), statistics.median(bwd_l)        # median: the reverse pass is ~10^3 launches, host noise shows
     lib.psvo_profile_enable(1)
     step(999)
@@ -542,11 +545,14 @@ def run_train_step(args, w, rank, world, local_rank, T=50, steps=5):
     if world > 1:
         torch.distributed.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    import gc
+    gc.collect(); gc.disable()
     for i, (a0, a1) in enumerate(ev):
         a0.record()
         z = sh.step(obs, None, seed=100 + i)
         a1.record()
     torch.cuda.synchronize()
+    gc.enable()
     t = torch.tensor([statistics.median(a0.elapsed_time(a1) for a0, a1 in ev)], device=dev, dtype=torch.float64)   # median: host-launch noise
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

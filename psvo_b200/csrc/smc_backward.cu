@@ -302,15 +302,46 @@ __global__ void __launch_bounds__(256) bwd_proposal_kernel(BwdArgs a) {
 // tcgen05 kernels; these two light kernels do what is left of a step per particle -- the upstream gradient of the network
 // output, the sigma statistics and the per-sequence reductions -- with the same formulas as the fused kernels above.
 // ------------------------------------------------------------------------------------------------------
-// one thread per ELEMENT (row, d): fully coalesced reads of mu and writes of G
+// one thread per FOUR consecutive columns of a row (Gaussian emission, Dy a multiple of 4; 128-bit loads and stores, the
+// particle's weight gradient computed once per four elements, 32-bit index arithmetic, reciprocal of sigma), else one thread per
+// element; fully coalesced reads of mu and writes of G either way
 __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
   __shared__ float sstat[32];
-  __shared__ float ssg[32];
+  __shared__ float ssg[32], sinv[32];
   const int Dy = a.Dy, N = a.N;
   const bool poisson = a.flags & PSVO_F_POISSON;
-  if (threadIdx.x < 32) { sstat[threadIdx.x] = 0.0f; ssg[threadIdx.x] = a.sig[SIG_G * 32 + threadIdx.x]; }
+  if (threadIdx.x < 32) {
+    const float v = a.sig[SIG_G * 32 + threadIdx.x];
+    sstat[threadIdx.x] = 0.0f; ssg[threadIdx.x] = v; sinv[threadIdx.x] = 1.0f / v;
+  }
   __syncthreads();
   const long long total = (long long)a.B * N * Dy;
+  if (!poisson && (Dy & 3) == 0 && total < (1LL << 31) && (256 % (Dy >> 2)) == 0) {
+    const int q4 = Dy >> 2;                                  // column groups per row
+    const int groups = (int)(total >> 2);
+    const int cg = (int)(threadIdx.x % q4);                  // the same column group in every iteration (256 and the stride are multiples of q4)
+    const float4 isg = make_float4(sinv[4 * cg], sinv[4 * cg + 1], sinv[4 * cg + 2], sinv[4 * cg + 3]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < groups; e += gridDim.x * 256) {
+      const int row = e / q4;
+      const int b = row / N, n = row - b * N;
+      const size_t bt = (size_t)b * a.T + a.t;
+      const float gl = particle_weight_grad(a, b, n, true);
+      const float4 y = __ldg(reinterpret_cast<const float4*>(a.obs + bt * Dy) + cg);
+      const float4 mu = reinterpret_cast<const float4*>(a.ext_mu)[e];
+      float4 g;
+      const float z0 = (y.x - mu.x) * isg.x, z1 = (y.y - mu.y) * isg.y, z2 = (y.z - mu.z) * isg.z, z3 = (y.w - mu.w) * isg.w;
+      g.x = gl * z0 * isg.x; g.y = gl * z1 * isg.y; g.z = gl * z2 * isg.z; g.w = gl * z3 * isg.w;
+      reinterpret_cast<float4*>(a.ext_g)[e] = g;
+      acc.x += gl * (z0 * z0 - 1.0f) * isg.x; acc.y += gl * (z1 * z1 - 1.0f) * isg.y;
+      acc.z += gl * (z2 * z2 - 1.0f) * isg.z; acc.w += gl * (z3 * z3 - 1.0f) * isg.w;
+    }
+    atomicAdd(&sstat[4 * cg], acc.x); atomicAdd(&sstat[4 * cg + 1], acc.y);
+    atomicAdd(&sstat[4 * cg + 2], acc.z); atomicAdd(&sstat[4 * cg + 3], acc.w);
+    __syncthreads();
+    if (threadIdx.x < Dy) { const float v = sstat[threadIdx.x]; if (v != 0.0f) atomicAdd(a.stats + (ST_SG * 2 + 1) * 32 + threadIdx.x, v); }
+    return;
+  }
   const bool fixed_d = (blockDim.x % Dy) == 0;        // then e % Dy is the same in every iteration of a thread
   float acc = 0.0f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -394,16 +425,17 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
           const float m2 = __ldg(a.mu2_all + bt * Dx + d);
           const float A = inv1[d] * mu1 + inv2[d] * m2;                   // m / sp
           const float m = sp[d] * A;
-          const float e = (X - m) / sp[d];
-          const float zf = (X - mu1) / s1[d];                             // f_lp = d1_mvn.log_prob(X): sf = s1, muf = mu1
-          float gX = r_gi[d] + r_gg[d] - gl * zf / s1[d];
+          const float isp = inv1[d] + inv2[d];                            // 1 / sp
+          const float e = (X - m) * isp;
+          const float zf = (X - mu1) * inv1[d];                           // f_lp = d1_mvn.log_prob(X): sf = s1, muf = mu1
+          float gX = r_gi[d] + r_gg[d] - gl * zf * inv1[d];
           if (a.g_Xs != nullptr) gX += a.g_Xs[(bt * N + n) * Dx + d];
-          st_sp[d] += gX * e + gl / sp[d] + gX * A;
-          st_sf[d] += gl * (zf * zf - 1.0f) / s1[d];
+          st_sp[d] += gX * e + gl * isp + gX * A;
+          st_sf[d] += gl * (zf * zf - 1.0f) * inv1[d];
           st_i1[d] += gX * sp[d] * mu1;
           st_i2[d] += gX * sp[d] * m2;
           gm2 = gX * sp[d] * inv2[d];
-          a.ext_g[id * Dx + d] = gX * sp[d] * inv1[d] + gl * zf / s1[d];  // via m, plus d f_lp / d muf (muf IS mu1)
+          a.ext_g[id * Dx + d] = gX * sp[d] * inv1[d] + gl * zf * inv1[d];  // via m, plus d f_lp / d muf (muf IS mu1)
         }
         if (uniform) {
           const float v = warp_sum(gm2);
