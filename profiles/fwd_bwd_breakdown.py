@@ -26,14 +26,20 @@ def step(seed, rec=None):
     torch.cuda.synchronize(); h3 = time.perf_counter()
     if rec is not None: rec.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), 1e3 * (h1 - h0), 1e3 * (h2 - h1), 1e3 * (h3 - h0)))
     return z
-for i in range(3): step(i)
+big = T >= 500                                   # full length: ~71 GB of filter outputs per call -- drop the previous call's before the next
+def run(seed, rec=None):
+    if big:
+        smc.last = None
+        torch.cuda.empty_cache()
+    return step(seed, rec)
+for i in range(1 if big else 3): run(i)
 rec = []
-for i in range(7): step(10 + i, rec)
+for i in range(2 if big else 7): run(10 + i, rec)
 med = [statistics.median(r[k] for r in rec) for k in range(5)]
 print("T=%d: device fwd %.2f ms, device bwd %.2f ms | host enqueue fwd %.2f, bwd %.2f | wall %.2f ms" % (T, *med))
 print("per-iteration device bwd:", [round(r[1], 1) for r in rec])
 lib.psvo_profile_enable(1)
-step(99); torch.cuda.synchronize()
+run(99); torch.cuda.synchronize()
 kms, kl = (C.c_double * 8)(), (C.c_int64 * 8)()
 lib.psvo_profile_read(kms, kl); lib.psvo_profile_enable(0)
 names = ["smc_propagate", "smc_resample", "mlp_rows", "sigma", "smc_backward", "ffbsi", "ops", "-"]

@@ -39,7 +39,9 @@ class SMCFilterFn(torch.autograd.Function):
         P = _unflatten(cfg["layout"], flat)
         r = Fn.smc_forward_raw(P, cfg["flags"], obs, pre_obs, pre_x0, cfg["N"], eps=eps, u=u, forced_anc=forced_anc,
                                seed=cfg["seed"], seq_offset=cfg["seq_offset"], out=cfg.get("out"))
-        ctx.cfg = cfg
+        # the node keeps only the scalars it needs: a reference to cfg (whose "last" holds this call's outputs, whose grad_fn is
+        # this node) would be a cycle that only the garbage collector frees -- gigabytes of particles per call until it runs
+        ctx.cfg = {k: cfg[k] for k in ("layout", "flags", "N", "seed", "seq_offset")}
         ctx.n_flat = len(flat)
         ctx.save_for_backward(obs, pre_obs, pre_x0, eps, r["Xs"], r["X_anc"], r["anc"], r["log_Ws"], r["lse"], *flat)
         for k in ("Xs", "X_anc", "anc", "log_Ws", "lse"):
@@ -84,7 +86,7 @@ class SmoothingFn(torch.autograd.Function):
         bs = Fn.ffbsi_forward_raw(P, fl, obs, bs_feat, pre_x0, r["Xs"], r["log_Ws"], r["lse"], cfg["M"], eps_bw=eps_bw,
                                   u_pick=u_pick, u_res=u_res, forced_pick=forced_pick, forced_anc2=forced_anc2,
                                   seed=cfg["seed"], seq_offset=cfg["seq_offset"])
-        ctx.cfg = cfg
+        ctx.cfg = {k: cfg[k] for k in ("layout", "flags", "N", "M", "seed", "seq_offset")}      # no reference to cfg["last"]: see SMCFilterFn
         ctx.fwd_keys = [k for k in ("bw_Xs", "pick", "f_lp", "g_lp", "Omega", "bw_log_W", "bw_X_anc", "anc2") if k in bs]
         opt = [eps, eps_bw]
         ctx.has_opt = [t is not None for t in opt]
