@@ -281,7 +281,8 @@ def run_ours(args, w, rank, world, local_rank):
                                          C.byref(Fn.params_struct(P, []))))
     kernel_name = {0: "smc_propagate_kernel (FP32, per step)", 1: "smc_filter_persistent_kernel (one launch per pass)",
                    2: "smc_propagate_tc_kernel<32> (tcgen05, per step)",
-                   3: "smc_filter_tc_persistent_kernel<32> (tcgen05, one launch per pass, resampling inside; opt-in PSVO_TC_PERSIST=1)"}.get(path, "?")
+                   3: "smc_filter_tc_persistent_kernel<32> (tcgen05, one launch per pass, resampling inside; opt-in PSVO_TC_PERSIST=1)",
+                   4: "smc_filter_cluster_kernel (FP32, one launch per pass, one thread-block cluster per sequence)"}.get(path, "?")
     roof.update({"kernel": kernel_name, "avg_launch_ms": prop_ms_avg, "peak_source": peak_src,
                  "alg_flop_per_launch": fl_launch, "alg_bytes_per_launch": by_launch,
                  "fp32_cuda_core_tflops": fl_launch / (prop_ms_avg * 1e-3) / 1e12,

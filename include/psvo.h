@@ -229,7 +229,9 @@ PSVO_API int psvo_fill_uniform(uint64_t seed, int32_t stream_id, int64_t first_p
    smc_resample_kernel), 1 = persistent whole-filter kernel (smc_filter_persistent_kernel, one launch per pass),
    2 = per-step tcgen05 kernel (smc_propagate_tc_kernel) + resampling kernel (smc_resample_lean_kernel when every sequence gets a
    CTA of its own and N >= 2048, else smc_resample_kernel), 3 = the opt-in persistent tcgen05 whole-filter kernel
-   (PSVO_TC_PERSIST=1: smc_filter_tc_persistent_kernel, resampling inside the launch); <0 on invalid arguments */
+   (PSVO_TC_PERSIST=1: smc_filter_tc_persistent_kernel, resampling inside the launch), 4 = cluster whole-filter kernel
+   (smc_filter_cluster_kernel: one launch per pass, one thread-block cluster per sequence; few sequences of many particles);
+   <0 on invalid arguments */
 PSVO_API int psvo_smc_forward_path(const psvo_dims* d, const psvo_params* p);
 PSVO_API int psvo_profile_enable(int on);
 PSVO_API int psvo_profile_read(double* ms_by_kind, int64_t* launches_by_kind);

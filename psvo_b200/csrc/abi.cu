@@ -204,8 +204,9 @@ PSVO_API int psvo_smc_forward_path(const psvo_dims* d, const psvo_params* p) {
     ResampleArgs ra; ra.N = d->N; ra.B = d->B; ra.T = d->T; ra.flags = d->flags;
     return tc_filter_persistent_supported(pa, ra) ? 3 : 2;
   }
-  size_t psm = 0; int pblk = 0;
-  return persistent_filter_supported(pa, plan, &psm, &pblk) ? 1 : 0;
+  size_t psm = 0; int pblk = 0, csz = 0;
+  if (persistent_filter_supported(pa, plan, &psm, &pblk)) return 1;
+  return cluster_filter_supported(pa, &csz, &pblk, &psm) ? 4 : 0;
 }
 
 PSVO_API size_t psvo_smc_workspace_bytes(const psvo_dims* d, const psvo_params* p) {
@@ -255,6 +256,8 @@ PSVO_API int psvo_smc_forward(const psvo_dims* d, const psvo_params* p, const fl
   {
     size_t psm = 0; int pblk = 0;
     if (persistent_filter_supported(pa, plan, &psm, &pblk)) return launch_filter_persistent(pa, ra, plan, st);
+    int csz = 0;
+    if (cluster_filter_supported(pa, &csz, &pblk, &psm)) { ra.skip_gather = 0; return launch_filter_cluster(pa, ra, st); }
   }
   // tensor-core path: the ancestor gather X_anc[t] = Xs[t][anc[t]] is folded into the propagate launch of t+1 (which
   // needs the parents anyway), so only the last step's resample launch moves particle states

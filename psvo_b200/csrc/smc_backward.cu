@@ -371,13 +371,13 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
 // t >= 1, f aliases d1 = q1:  mu1 = MLP q1(X_anc[t-1]) from ext_mu; writes d/dmu1 to ext_g
 __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
   __shared__ float sstat[4 * 32];
-  __shared__ float s1[PSVO_MAX_DX], sp[PSVO_MAX_DX], inv1[PSVO_MAX_DX], inv2[PSVO_MAX_DX];
+  __shared__ float sp[PSVO_MAX_DX], inv1[PSVO_MAX_DX], inv2[PSVO_MAX_DX];
   const int Dx = a.Dx, N = a.N;
   for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) sstat[i] = 0.0f;
   if (threadIdx.x < PSVO_MAX_DX) {
     const int d = threadIdx.x;
     const float v1 = d < Dx ? __ldg(a.sig + SIG_Q1 * 32 + d) : 1.0f, v2 = d < Dx ? __ldg(a.sig + SIG_Q2 * 32 + d) : 1.0f;
-    s1[d] = v1; inv1[d] = 1.0f / v1; inv2[d] = 1.0f / v2; sp[d] = 1.0f / (1.0f / v1 + 1.0f / v2);
+    inv1[d] = 1.0f / v1; inv2[d] = 1.0f / v2; sp[d] = 1.0f / (1.0f / v1 + 1.0f / v2);
   }
   __syncthreads();
   float st_sp[PSVO_MAX_DX], st_i1[PSVO_MAX_DX], st_i2[PSVO_MAX_DX], st_sf[PSVO_MAX_DX];

@@ -63,6 +63,9 @@ int launch_resample(const ResampleArgs& a, cudaStream_t st);
 // persistent whole-filter kernel (one launch per pass, one CTA per sequence): small N / few sequences
 bool persistent_filter_supported(const PropArgs& a, const PropPlan& pl, size_t* smem_out, int* block_out);
 int launch_filter_persistent(PropArgs pa, const ResampleArgs& ra, const PropPlan& pl, cudaStream_t st);
+// cluster whole-filter kernel (one launch per pass, one thread-block cluster per sequence): few sequences of many particles
+bool cluster_filter_supported(const PropArgs& a, int* csize_out, int* block_out, size_t* smem_out);
+int launch_filter_cluster(PropArgs pa, const ResampleArgs& ra, cudaStream_t st);
 
 // generic row MLP (mlp_rows.cu)
 int launch_mlp_rows_forward(const psvo_mlp& net, const float* x, int64_t rows, float* mu, cudaStream_t st);

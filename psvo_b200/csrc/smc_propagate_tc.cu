@@ -350,7 +350,7 @@ __device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, con
   ag.w1h = tc_opaque(sm_base + L.w1g_hi); ag.w1l = tc_opaque(sm_base + L.w1g_lo); ag.w1b = tc_opaque(sm_base + L.w1g_b);
   ag.w2h = tc_opaque(sm_base + L.w2g_hi); ag.w2l = tc_opaque(sm_base + L.w2g_lo);
   uint32_t par = 0;
-  if (PERSIST) {
+  if constexpr (PERSIST) {
     // tiles are handed out dynamically: the compute group leaves a command word next to its first operand (published by the
     // A1 barrier's release / acquire): 0 = both networks, 1 = emission network only (t = 0), 2 = no more tiles
     const uint32_t cmd_addr = tc_opaque(sm_base + (uint32_t)work);         // `work` carries the shared-memory offset of the group's word
@@ -367,11 +367,11 @@ __device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, con
         tc_mma_net<NPG, false>(ag, lbo1, tb, bars, nst, par);
       }
     }
-    return;
-  }
-  for (int wi = blockIdx.x * kTcGroups + grp; wi < items; wi += gridDim.x * kTcGroups) {
-    if (first_net == 0) tc_mma_net<16>(aq, lbo1, tb, bars, nst, par);
-    tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
+  } else {
+    for (int wi = blockIdx.x * kTcGroups + grp; wi < items; wi += gridDim.x * kTcGroups) {
+      if (first_net == 0) tc_mma_net<16>(aq, lbo1, tb, bars, nst, par);
+      tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
+    }
   }
 }
 
