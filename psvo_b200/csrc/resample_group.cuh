@@ -60,12 +60,13 @@ struct RgBlockBar {            // the whole CTA
 __device__ __forceinline__ void rg_bar(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
 
 // sequence b, time t; NT threads (a multiple of 32; g = thread index, bar = their barrier).  Writes anc[b][t][:], lse[b][t],
-// accumulates logZ_b[b] (and logWbar when resampling is off); sAnc (optional, N ints of shared memory) also receives the
-// ancestors for a gather by the caller.  LDCG: log_Ws[b][t][:] was written by other SMs during this launch -> read through L2.
+// accumulates logZ_b[b] (and logWbar when resampling is off); sAnc (optional, shared memory) also receives the ancestors
+// (sAnc[n - c_lo]) for a gather by the caller.  [c_lo, c_hi): the children this caller serves (a CTA of a cluster rebuilds the
+// whole CDF but resamples only its own range; write_stats: only one of them stores lse / logZ_b).  LDCG: log_Ws[b][t][:] was written by other SMs during this launch -> read through L2.
 // region: rg_smem_bytes(N, NT) bytes; the caller owns the first 64 bytes (lock, flags).
 template <bool LDCG, typename Bar>
 __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int t, unsigned char* region, int g, const int NT, Bar bar,
-                                              int* sAnc = nullptr) {
+                                              int* sAnc = nullptr, int c_lo = 0, int c_hi = 0x7fffffff, bool write_stats = true) {
   const int NW = NT >> 5;
   const int N = a.N;
   const int lane = g & 31, w = g >> 5;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
 
   // logsumexp from the same integer total (identical to resample_body)
   const float lse = mx + (logf((float)total) - 32.0f * kLn2);
-  if (g == 0) {
+  if (g == 0 && write_stats) {
     if (a.lse != nullptr) a.lse[bt] = lse;
     if (a.logZ_b != nullptr) a.logZ_b[b] = (t == 0 ? 0.0f : a.logZ_b[b]) + lse;
   }
@@ -190,7 +191,9 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
   // ---- children: four CONSECUTIVE children per thread at a time (their uniforms are the four words of one Philox block)
   const bool systematic = a.flags & PSVO_F_SYSTEMATIC;
   const uint64_t gbase = ((uint64_t)(a.seq_offset + b) * a.T + t) * N;
-  for (int n0 = 4 * g; n0 < N; n0 += 4 * NT) {
+  c_hi = c_hi < N ? c_hi : N;
+  const bool vec_store = ((N | c_lo) & 3) == 0;
+  for (int n0 = c_lo + 4 * g; n0 < c_hi; n0 += 4 * NT) {
     unsigned long long thr[4];
     int anc[4];
     bool search[4];
@@ -204,7 +207,7 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
     for (int k = 0; k < 4; ++k) {
       const int n = n0 + k;
       anc[k] = n; search[k] = false; thr[k] = 0ull;
-      if (n < N && resample) {
+      if (n < c_hi && resample) {
         if (a.forced_anc != nullptr) {
           const int f = a.forced_anc[bt * N + n];
           anc[k] = f < 0 ? 0 : (f >= N ? N - 1 : f);
@@ -242,17 +245,17 @@ __device__ __forceinline__ void resample_lean(const ResampleArgs& a, int b, int 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (search[k]) anc[k] = pos[k] < N ? pos[k] : N - 1;
-      if (!resample && n0 + k < N) a.logWbar[(size_t)b * N + n0 + k] = sLW[n0 + k + ((n0 + k) >> sh)] - lse;   // SVO.py:102,156
+      if (!resample && n0 + k < c_hi) a.logWbar[(size_t)b * N + n0 + k] = sLW[n0 + k + ((n0 + k) >> sh)] - lse;   // SVO.py:102,156
     }
-    if ((N & 3) == 0) {
+    if (vec_store && n0 + 4 <= c_hi) {
       *reinterpret_cast<int4*>(a.anc + bt * N + n0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (n0 + k < N) a.anc[bt * N + n0 + k] = anc[k];
+      for (int k = 0; k < 4; ++k) if (n0 + k < c_hi) a.anc[bt * N + n0 + k] = anc[k];
     }
     if (sAnc != nullptr) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (n0 + k < N) sAnc[n0 + k] = anc[k];
+      for (int k = 0; k < 4; ++k) if (n0 + k < c_hi) sAnc[n0 + k - c_lo] = anc[k];
     }
   }
 }

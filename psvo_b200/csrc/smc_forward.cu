@@ -713,6 +713,8 @@ __global__ void __launch_bounds__(256, 1) smc_filter_cluster_kernel(PropArgs pa,
     const StepConsts<DXP>* C = t == 0 ? C0 : C1;
     for (int n0 = n_lo; n0 < n_hi; n0 += tile) propagate_tile<DXP, DYP, 1>(pa, C, q1s, fs, gs, scratch, b, n0, t, n_hi);
     cluster_sync_all();                                      // log_W_t / X_t of the whole sequence written and visible
+    // (the guide-table routine of resample_group.cuh restricted to the CTA's children was tried here: 14.9 vs 12.95 ms per
+    // config-4 pass -- every CTA would build the whole table for an eighth of the children)
     resample_body<false>(ra, b, rank, csize, t, rs_smem, sscr, fscr);
     __syncthreads();                                         // X_anc_t / logWbar of this CTA's own children written
   }
@@ -819,6 +821,17 @@ bool cluster_filter_supported(const PropArgs& a, int* csize_out, int* block_out,
   while (csize > 1 && (a.N / csize < 128 || (long long)a.B * csize > num_sms())) csize /= 2;
   if (csize < 2) return false;
   const int chunk = (a.N + csize - 1) / csize;
+  {
+    // like the persistent kernel: only while one step of one CTA's particles is a small amount of work (with heavy networks
+    // the per-step launches spread a sequence over more SMs than a cluster has)
+    auto macs = [](const psvo_mlp& net) {
+      long long m = 0; int in = net.d_in;
+      for (int k = 0; k < net.n_hidden; ++k) { m += (long long)in * net.width[k]; in = net.width[k]; }
+      return m + (long long)in * net.d_out;
+    };
+    const long long instr = 300 + macs(a.q1) + macs(a.g) + (sep_f ? macs(a.f) : 0);
+    if ((long long)chunk * instr > 600000) return false;
+  }
   int block = chunk < 256 ? ((chunk + 31) & ~31) : 256;
   const size_t total = cluster_prop_floats(a) * sizeof(float) + (size_t)a.N * 12 + (size_t)chunk * 4 + 16;
   if (total > 200 * 1024) return false;

@@ -86,3 +86,44 @@ def test_forced_thread_contiguous_kernel_on_golden_and_oracle_cases():
                        env=env, capture_output=True, text=True, cwd=ROOT, timeout=850)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1500:]
+
+
+def _run_cfg(Dx_, Dy_, H_, N, B, T, poisson=False, resample=True, seed=9):
+    from psvo_b200 import functional as Fn
+    F = O.Flags(poisson_emission=poisson, resample_particles=resample)
+    P = O.make_params(4, Dx_, Dy_, Dy_, Dy_, H_, F)
+    g = torch.Generator().manual_seed(23)
+    obs = torch.randn(B, T, Dy_, generator=g).abs() if poisson else torch.randn(B, T, Dy_, generator=g)
+    fw = Fn.smc_forward_raw(to_dev(P, DEV), flags_of(F), obs.to(DEV), obs.to(DEV), obs[:, 0].contiguous().to(DEV), N, seed=seed)
+    return {k: fw[k].cpu() for k in ("Xs", "X_anc", "anc", "log_Ws", "lse", "logZ_b")}
+
+
+CLUSTER_CASES = [(4, 1, [64], 2048, 1, 6, True, True),        # BASELINE config 4: eight CTAs x 256 particles
+                 (5, 7, [24], 777, 3, 4, False, True),         # ragged: four CTAs x 195 particles (224 threads)
+                 (3, 3, [32], 1500, 2, 5, False, False)]       # IWAE: no resampling, log Wbar carried per CTA
+
+
+@pytest.mark.timeout(600)
+def test_cluster_filter_kernel_is_bit_identical_to_per_step_launches(tmp_path):
+    """smc_filter_cluster_kernel (one thread-block cluster per sequence, one cluster barrier per time step) against the
+    per-step launches of the same device code (PSVO_CLUSTER=0 in a subprocess)."""
+    if os.environ.get("PSVO_CLUSTER") == "0":
+        pytest.skip("inside the per-step re-run")
+    got = [_run_cfg(*c) for c in CLUSTER_CASES]
+    dump = str(tmp_path / "perstep.pt")
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_resample_paths as m; "
+            "torch.save([m._run_cfg(*c) for c in m.CLUSTER_CASES], %r)") % (ROOT, os.path.join(ROOT, "tests"), dump)
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PSVO_CLUSTER="0"), capture_output=True, text=True,
+                       cwd=ROOT, timeout=500)
+    assert p.returncode == 0, p.stderr[-3000:]
+    ref = torch.load(dump)
+    for c, a, r in zip(CLUSTER_CASES, got, ref):
+        for k in ("anc", "Xs", "X_anc", "log_Ws", "lse", "logZ_b"):
+            assert torch.equal(a[k], r[k]), (c, k)
+    # and the path really is the cluster kernel for the config-4 shape
+    import ctypes as C
+    from psvo_b200 import functional as Fn, _lib
+    F = O.Flags(poisson_emission=True)
+    P = to_dev(O.make_params(4, 4, 1, 1, 1, [64], F), DEV)
+    path = _lib.load().psvo_smc_forward_path(C.byref(Fn.make_dims(2048, 1, 6, 4, 1, 1, 1, flags_of(F))), C.byref(Fn.params_struct(P, [])))
+    assert path == 4, path
