@@ -96,6 +96,7 @@ struct FfbsiArgs {
   unsigned long long seed;
   int N, M, B, T, Dx, Dy, t, seq_offset, IL;
   unsigned flags;
+  int t_loop = 0;            // 1: ONE launch walks t = T-1 .. 0 itself (mu_f then points at the (T, N, Dx) means of all steps)
 };
 
 constexpr int kPairChunk = 128;
@@ -103,10 +104,13 @@ constexpr int kPairChunk = 128;
 template <int DXP, int DYP>
 __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int Dx = a.Dx, Dy = a.Dy, N = a.N, M = a.M, T = a.T, t = a.t;
+  const int Dx = a.Dx, Dy = a.Dy, N = a.N, M = a.M, T = a.T;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP, two_q = a.flags & PSVO_F_TWO_Q, poisson = a.flags & PSVO_F_POISSON;
   const bool wr = a.flags & PSVO_F_WITH_RESAMPLING;
-  const bool last = t == T - 1, first = t == 0;
+  // PSVO trajectories never interact in the backward simulation (candidate x~[m,i] depends on trajectory i's own x_{t+1} and on
+  // the FILTER's particles only, PSVO.py:116-156), so with the transition means of all steps precomputed a CTA can walk its
+  // trajectories through all T steps by itself: the whole pass is ONE launch without any cross-CTA synchronisation
+  const bool loop = a.t_loop != 0;
 
   MlpS<DXP, DXP> fs;
   MlpS<DXP, DYP> gs;
@@ -115,34 +119,17 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
   float* sf = p; p += DXP;  float* sinit = p; p += DXP; float* sg = p; p += 32;
   float* lds = p; p += 4;                     // logdet: proposal, f, g, init
   const bool ext = a.F_ext != nullptr;        // candidate densities precomputed on tensor cores: no networks staged here
-  if (!last && !ext) p = mlp_stage<DXP, DXP>(a.f, p, fs);
+  if ((loop || a.t != T - 1) && !ext) p = mlp_stage<DXP, DXP>(a.f, p, fs);
   if (!ext) p = mlp_stage<DXP, DYP>(a.g, p, gs);
   MlpS<DXP, DXP> qis;
-  const bool fuse_q1i = a.mu1i_next != nullptr && !first;
-  if (fuse_q1i) p = mlp_stage<DXP, DXP>(a.q1_inv, p, qis);
+  if (a.mu1i_next != nullptr && (loop || a.t != 0)) p = mlp_stage<DXP, DXP>(a.q1_inv, p, qis);
   float* sMu = p; p += kPairChunk * DXP;      // mu_f[j] / s_f
   float* sWb = p; p += kPairChunk;            // normalised log weight of j
   float* sCand = p; p += blockDim.x * 5;      // omega | f | g | q | P per candidate
   float* sX = p;                              // [blockDim][DXP] candidate particles
 
-  if (threadIdx.x < DXP) {
-    const int d = threadIdx.x;
-    const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
-    inv1[d] = 1.0f / s1; inv2[d] = 1.0f / s2;
-    sp[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
-    sf[d] = a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
-    sinit[d] = a.sig[((boot && two_q) ? SIG_Q0 : (boot ? SIG_Q1 : SIG_F)) * 32 + d];
-  }
   for (int i = threadIdx.x; i < 32; i += blockDim.x) sg[i] = a.sig[SIG_G * 32 + i];
-  griddep_entry();                       // networks and sigmas (constant over the pass) staged; the previous step's outputs are read below
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-    for (int d = 0; d < Dx; ++d) { l0 += logf(sp[d]); l1 += logf(sf[d]); l3 += logf(sinit[d]); }
-    if (!poisson) for (int d = 0; d < Dy; ++d) l2 += logf(sg[d]);
-    lds[0] = l0; lds[1] = l1; lds[2] = l2; lds[3] = l3;
-  }
-  __syncthreads();
+  griddep_entry();                       // networks (constant over the pass) staged; the previous step's outputs are read below
   const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
   const float logM = logf((float)M);
 
@@ -151,7 +138,30 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
   const int tiles_per_seq = (N + IL - 1) / IL;
   const int work = a.B * tiles_per_seq;
 
-  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+  for (int wi = blockIdx.x; wi < work; wi += gridDim.x)
+  for (int t = loop ? T - 1 : a.t; t >= (loop ? 0 : a.t); --t) {
+    const bool last = t == T - 1, first = t == 0;
+    const bool fuse_q1i = a.mu1i_next != nullptr && !first;
+    const float* mu_f_t = (loop && t >= 1) ? a.mu_f + (size_t)(t - 1) * N * Dx : a.mu_f;
+    // per-step constants (the proposal of the last step has its own stddev); the barrier also closes the previous step of
+    // this tile: its picks and proposal means (global memory, written by this CTA) are visible to the whole CTA
+    __syncthreads();
+    if (threadIdx.x < DXP) {
+      const int d = threadIdx.x;
+      const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
+      inv1[d] = 1.0f / s1; inv2[d] = 1.0f / s2;
+      sp[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
+      sf[d] = a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+      sinit[d] = a.sig[((boot && two_q) ? SIG_Q0 : (boot ? SIG_Q1 : SIG_F)) * 32 + d];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      for (int d = 0; d < Dx; ++d) { l0 += logf(sp[d]); l1 += logf(sf[d]); l3 += logf(sinit[d]); }
+      if (!poisson) for (int d = 0; d < Dy; ++d) l2 += logf(sg[d]);
+      lds[0] = l0; lds[1] = l1; lds[2] = l2; lds[3] = l3;
+    }
+    __syncthreads();
     const int b = wi / tiles_per_seq;
     const int i = (wi - b * tiles_per_seq) * IL + il;
     const bool live = il < IL && i < N;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
         __syncthreads();
         for (int q = threadIdx.x; q < kPairChunk * DXP; q += blockDim.x) {
           const int jj = q / DXP, d = q - jj * DXP;
-          sMu[q] = (j0 + jj < N && d < Dx) ? a.mu_f[((size_t)b * N + j0 + jj) * Dx + d] / sf[d] : 0.0f;
+          sMu[q] = (j0 + jj < N && d < Dx) ? mu_f_t[((size_t)b * N + j0 + jj) * Dx + d] / sf[d] : 0.0f;
         }
         for (int q = threadIdx.x; q < kPairChunk; q += blockDim.x)
           sWb[q] = j0 + q < N ? a.log_Ws[(bt - 1) * N + j0 + q] - lse_prev : -INFINITY;
@@ -506,7 +516,21 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
                                          : launch_particle_mlp<16>(fd.net, Xs, (long long)N * Dx, T, N, Dx, w.mu_f_all, st));
     if (rc0) return rc0;
   }
-  for (int t = T - 1; t >= 0; --t) {
+  // PSVO on the FP32 kernels with the transition means of all steps at hand (batch 1): the whole backward simulation is ONE
+  // launch, every CTA walking its trajectories through all T steps (PSVO_FFBSI_LOOP=0 keeps one launch per step)
+  static const bool loop_off = getenv("PSVO_FFBSI_LOOP") != nullptr && getenv("PSVO_FFBSI_LOOP")[0] == '0';
+  const bool whole_pass = !loop_off && fuse_q1i && !pair_tc && !cand_tc && w.mu_f_all != nullptr && T >= 2;
+  if (whole_pass) {
+    a.t = T - 1; a.t_loop = 1; a.mu_f = w.mu_f_all; a.P_ext = nullptr;
+    int rc = -1;
+#define PSVO_CASE_FL(X, Y) if (DXP == X && DYP == Y) rc = launch_step_t<X, Y>(a, block, grid, smem, st);
+    PSVO_CASE_FL(4, 4) PSVO_CASE_FL(4, 8) PSVO_CASE_FL(4, 16) PSVO_CASE_FL(4, 32)
+    PSVO_CASE_FL(8, 4) PSVO_CASE_FL(8, 8) PSVO_CASE_FL(8, 16) PSVO_CASE_FL(8, 32)
+    PSVO_CASE_FL(16, 4) PSVO_CASE_FL(16, 8) PSVO_CASE_FL(16, 16) PSVO_CASE_FL(16, 32)
+#undef PSVO_CASE_FL
+    if (rc) return rc;
+  }
+  for (int t = whole_pass ? -1 : T - 1; t >= 0; --t) {
     a.t = t;
     int rc = 0;
     if (t >= 1 && w.mu_f_all != nullptr) {
