@@ -400,15 +400,15 @@ int launch_mlp_bwd_tc_stage(const psvo_mlp& net, unsigned char* image, cudaStrea
 // `scatter` (then the caller zero-fills it).  grads are accumulated.
 int launch_mlp_bwd_tc(const psvo_mlp& net, const unsigned char* image, const float* x, long long x_seq_stride, const float* g,
                       int B, int N, float* gx, const int* scatter, long long scatter_seq_stride, const psvo_mlp_grad& grads,
-                      unsigned int* gmax_bits, cudaStream_t st) {
+                      unsigned int* gmax_bits, cudaStream_t st, bool gmax_ready) {
   const long long rows = (long long)B * N;
   PSVO_REQUIRE(mlp_bwd_tc_supported(net, rows), "tensor-core MLP reverse mode: unsupported shape");
   const int NP = net.d_out <= 16 ? 16 : 32;
   const BtSmem L = bt_layout(net.width[0], NP);
   const size_t smem = L.total + 128;
   PSVO_REQUIRE(smem <= 227 * 1024, "tensor-core MLP reverse mode: %zu B of shared memory", smem);
-  PSVO_CUDA(cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned int), st));
-  {
+  if (!gmax_ready) {                     // the caller's kernel that wrote G did not track max |G|
+    PSVO_CUDA(cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned int), st));
     ProfScope ps_(PK_BWD, st);
     const long long n = rows * net.d_out;
     long long grid = (n + 255) / 256; if (grid > 4LL * num_sms()) grid = 4LL * num_sms();

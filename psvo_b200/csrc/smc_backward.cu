@@ -42,6 +42,7 @@ struct BwdArgs {
   float* gmu0;       // (B,Dx)
   float* gmuf0;      // (B,Dx)
   float* stats;      // [ST_SLOTS*2][32]
+  unsigned int* gmax = nullptr;   // tensor-core path: max |ext_g| of the launch (bit pattern; mlp_bwd_tc's operand scale), or NULL
   int N, B, T, Dx, Dy, t;
   unsigned flags;
 };
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
     const int cg = (int)(threadIdx.x % q4);                  // the same column group in every iteration (256 and the stride are multiples of q4)
     const float4 isg = make_float4(sinv[4 * cg], sinv[4 * cg + 1], sinv[4 * cg + 2], sinv[4 * cg + 3]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gabs = 0.0f;
     for (int e = blockIdx.x * 256 + threadIdx.x; e < groups; e += gridDim.x * 256) {
       const int row = e / q4;
       const int b = row / N, n = row - b * N;
@@ -333,8 +335,13 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
       const float z0 = (y.x - mu.x) * isg.x, z1 = (y.y - mu.y) * isg.y, z2 = (y.z - mu.z) * isg.z, z3 = (y.w - mu.w) * isg.w;
       g.x = gl * z0 * isg.x; g.y = gl * z1 * isg.y; g.z = gl * z2 * isg.z; g.w = gl * z3 * isg.w;
       reinterpret_cast<float4*>(a.ext_g)[e] = g;
+      gabs = fmaxf(fmaxf(gabs, fmaxf(fabsf(g.x), fabsf(g.y))), fmaxf(fabsf(g.z), fabsf(g.w)));
       acc.x += gl * (z0 * z0 - 1.0f) * isg.x; acc.y += gl * (z1 * z1 - 1.0f) * isg.y;
       acc.z += gl * (z2 * z2 - 1.0f) * isg.z; acc.w += gl * (z3 * z3 - 1.0f) * isg.w;
+    }
+    if (a.gmax != nullptr) {                                 // the reverse GEMM kernel's operand scale: no pass of its own over G
+      gabs = warp_max(gabs);
+      if ((threadIdx.x & 31) == 0 && gabs > 0.0f) atomicMax(a.gmax, __float_as_uint(gabs));
     }
     atomicAdd(&sstat[4 * cg], acc.x); atomicAdd(&sstat[4 * cg + 1], acc.y);
     atomicAdd(&sstat[4 * cg + 2], acc.z); atomicAdd(&sstat[4 * cg + 3], acc.w);
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
     return;
   }
   const bool fixed_d = (blockDim.x % Dy) == 0;        // then e % Dy is the same in every iteration of a thread
-  float acc = 0.0f;
+  float acc = 0.0f, gabs = 0.0f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long row = e / Dy;
     const int d = (int)(e - row * Dy);
@@ -354,14 +361,20 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
     const float mu = a.ext_mu[e];
     if (poisson) {
       const float z = y - (softplus(mu) + 1e-6f);
-      a.ext_g[e] = gl * z * sigmoidf(mu);
+      const float gv = gl * z * sigmoidf(mu);
+      a.ext_g[e] = gv; gabs = fmaxf(gabs, fabsf(gv));
     } else {
       const float sg = ssg[d];
       const float z = (y - mu) / sg;
-      a.ext_g[e] = gl * z / sg;
+      const float gv = gl * z / sg;
+      a.ext_g[e] = gv; gabs = fmaxf(gabs, fabsf(gv));
       const float st = gl * (z * z - 1.0f) / sg;
       if (fixed_d) acc += st; else atomicAdd(&sstat[d], st);
     }
+  }
+  if (a.gmax != nullptr) {
+    gabs = warp_max(gabs);
+    if ((threadIdx.x & 31) == 0 && gabs > 0.0f) atomicMax(a.gmax, __float_as_uint(gabs));
   }
   if (!poisson && fixed_d && acc != 0.0f) atomicAdd(&sstat[threadIdx.x % Dy], acc);
   __syncthreads();
@@ -383,6 +396,7 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
   float st_sp[PSVO_MAX_DX], st_i1[PSVO_MAX_DX], st_i2[PSVO_MAX_DX], st_sf[PSVO_MAX_DX];
 #pragma unroll
   for (int d = 0; d < PSVO_MAX_DX; ++d) st_sp[d] = st_i1[d] = st_i2[d] = st_sf[d] = 0.0f;
+  float gabs = 0.0f;
   const long long rows = (long long)a.B * N;
   const long long rows_pad = (rows + 31) / 32 * 32;                       // whole warps iterate together (shuffles below)
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < rows_pad; idx += (long long)gridDim.x * blockDim.x) {
@@ -435,7 +449,8 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
           st_i1[d] += gX * sp[d] * mu1;
           st_i2[d] += gX * sp[d] * m2;
           gm2 = gX * sp[d] * inv2[d];
-          a.ext_g[id * Dx + d] = gX * sp[d] * inv1[d] + gl * zf * inv1[d];  // via m, plus d f_lp / d muf (muf IS mu1)
+          const float gv = gX * sp[d] * inv1[d] + gl * zf * inv1[d];        // via m, plus d f_lp / d muf (muf IS mu1)
+          a.ext_g[id * Dx + d] = gv; gabs = fmaxf(gabs, fabsf(gv));
         }
         if (uniform) {
           const float v = warp_sum(gm2);
@@ -445,6 +460,10 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
         }
       }
     }
+  }
+  if (a.gmax != nullptr) {
+    gabs = warp_max(gabs);
+    if ((threadIdx.x & 31) == 0 && gabs > 0.0f) atomicMax(a.gmax, __float_as_uint(gabs));
   }
 #pragma unroll
   for (int d = 0; d < PSVO_MAX_DX; ++d) {
@@ -715,26 +734,28 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
         fa.muq = w.tc_muq; fa.mug = w.tc_mu; fa.B = B; fa.N = N; fa.Dx = Dx; fa.Dy = d->Dy; fa.H = a.g.width[0];
         if ((rc = launch_tc_fwd2(fa, st))) return rc;
       }
-      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g;
+      // max |G| of both upstream gradients (mlp_bwd_tc's operand scales) comes out of the kernels that write G
+      PSVO_CUDA(cudaMemsetAsync(w.gmax, 0, 2 * sizeof(unsigned int), st));
+      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g; a.gmax = w.gmax;
       {
         ProfScope ps_(PK_BWD, st);
         emission_grad_kernel<<<light_grid, 256, 0, st>>>(a);
         PSVO_LAUNCH_CHECK();
       }
-      if ((rc = launch_mlp_bwd_tc(a.g, w.img_g, Xt, sstr, w.tc_g, B, N, w.gXg, nullptr, 0, a.gg, w.gmax, st))) return rc;
+      if ((rc = launch_mlp_bwd_tc(a.g, w.img_g, Xt, sstr, w.tc_g, B, N, w.gXg, nullptr, 0, a.gg, w.gmax, st, true))) return rc;
       // ---- proposal side
       if (t > 0) {
         const float* Xp = X_anc + (size_t)(t - 1) * N * Dx;
-        a.ext_mu = w.tc_muq;
+        a.ext_mu = w.tc_muq; a.gmax = w.gmax + 1;
         {
           ProfScope ps_(PK_BWD, st);
           proposal_grad_kernel<<<light_grid, 256, 0, st>>>(a);
           PSVO_LAUNCH_CHECK();
         }
         if ((rc = launch_mlp_bwd_tc(a.q1, w.img_q1, Xp, sstr, w.tc_g, B, N, gXout, anc + (size_t)(t - 1) * N, (long long)T * N,
-                                    a.gq1, w.gmax, st))) return rc;
+                                    a.gq1, w.gmax + 1, st, true))) return rc;
       } else {
-        a.ext_mu = nullptr; a.ext_g = nullptr;             // t = 0: no per-particle proposal network (q0 is per sequence)
+        a.ext_mu = nullptr; a.ext_g = nullptr; a.gmax = nullptr;   // t = 0: no per-particle proposal network (q0 is per sequence)
         rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP, smP), smP, st)
                       : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
                                   : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
@@ -748,7 +769,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
       const size_t pitch = (size_t)T * N * Dx * sizeof(float), width = (size_t)N * Dx * sizeof(float);
       PSVO_CUDA(cudaMemcpy2DAsync(w.rows_x, width, Xs + (size_t)t * N * Dx, pitch, width, B, cudaMemcpyDeviceToDevice, st));
       if (int e = launch_mlp_rows_forward(a.g, w.rows_x, (int64_t)BN, w.tc_mu, st)) return e;
-      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g;
+      a.ext_mu = w.tc_mu; a.ext_g = w.tc_g; a.gmax = nullptr;
       {
         ProfScope ps_(PK_BWD, st);
         emission_grad_kernel<<<light_grid, 256, 0, st>>>(a);

@@ -141,7 +141,7 @@ size_t mlp_bwd_tc_image_bytes(const psvo_mlp& net);
 int launch_mlp_bwd_tc_stage(const psvo_mlp& net, unsigned char* image, cudaStream_t st);
 int launch_mlp_bwd_tc(const psvo_mlp& net, const unsigned char* image, const float* x, long long x_seq_stride, const float* g,
                       int B, int N, float* gx, const int* scatter, long long scatter_seq_stride, const psvo_mlp_grad& grads,
-                      unsigned int* gmax_bits, cudaStream_t st);
+                      unsigned int* gmax_bits, cudaStream_t st, bool gmax_ready = false);   // gmax_ready: *gmax_bits already holds max |g|
 
 // tensor-core (tcgen05) one-hidden-layer MLP over particle rows (tc_mlp.cu)
 bool tc_mlp_supported(const psvo_mlp& net);
