@@ -952,6 +952,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
 // Plain forward of the two per-particle networks for the reverse pass (smc_backward.cu recomputes the network outputs
 // instead of storing them):  mu_q = MLP q1(xq rows), mu_g = MLP g(xg rows), same pipeline as smc_propagate_tc_kernel.
 // ------------------------------------------------------------------------------------------------------
+// one particle row in / 16 output columns out: 128-bit accesses when the width allows (rows are 16-byte aligned then)
+__device__ __forceinline__ void tc_fwd2_load_row(const float* __restrict__ src, int Dx, bool live, float (&x)[16]) {
+  if (Dx == 16) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4 q = live ? reinterpret_cast<const float4*>(src)[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
+  }
+}
+__device__ __forceinline__ void tc_fwd2_store_row(float* __restrict__ dst, int D, int c0, const float (&mu)[16], const float* __restrict__ bias) {
+  if ((D & 3) == 0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (c0 + 4 * v < D)
+        reinterpret_cast<float4*>(dst + c0)[v] = make_float4(fmaf(mu[4 * v], kWUnscale, bias[c0 + 4 * v]), fmaf(mu[4 * v + 1], kWUnscale, bias[c0 + 4 * v + 1]),
+                                                             fmaf(mu[4 * v + 2], kWUnscale, bias[c0 + 4 * v + 2]), fmaf(mu[4 * v + 3], kWUnscale, bias[c0 + 4 * v + 3]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (c0 + k < D) dst[c0 + k] = fmaf(mu[k], kWUnscale, bias[c0 + k]);
+  }
+}
+
 template <int NPG>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -985,31 +1011,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
       float x[16];
       if (with_q) {
         const float* src = a.xq + (long long)b * a.x_seq_stride + (long long)n * Dx;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
+        tc_fwd2_load_row(src, Dx, live, x);
         tc_mlp_compute(g, x, nchunk);
         float mu[16];
         tc::tmem_ld16(g.tb + kColD2, mu);
-        if (live) {
-          float* dst = a.muq + r * Dx;
-#pragma unroll
-          for (int d = 0; d < 16; ++d) if (d < Dx) dst[d] = fmaf(mu[d], kWUnscale, sb2q[d]);
-        }
+        if (live) tc_fwd2_store_row(a.muq + r * Dx, Dx, 0, mu, sb2q);
       }
       {
         const float* src = a.xg + (long long)b * a.x_seq_stride + (long long)n * Dx;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) x[d] = (live && d < Dx) ? src[d] : 0.0f;
+        tc_fwd2_load_row(src, Dx, live, x);
         tc_mlp_compute(g, x, nchunk);
 #pragma unroll
         for (int c0 = 0; c0 < NPG; c0 += 16) {
           float mu[16];
           tc::tmem_ld16(g.tb + kColD2 + c0, mu);
-          if (live) {
-            float* dst = a.mug + r * Dy;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) if (c0 + k < Dy) dst[c0 + k] = fmaf(mu[k], kWUnscale, sb2g[c0 + k]);
-          }
+          if (live) tc_fwd2_store_row(a.mug + r * Dy, Dy, c0, mu, sb2g);
         }
       }
     }
