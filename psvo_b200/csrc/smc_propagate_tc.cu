@@ -785,6 +785,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) smc_filter_tc_persistent_kernel
 // image holds f in the "q" slot); the candidate is recomputed from eps_bw / Philox exactly like ffbsi_step_kernel does.
 // Outputs f_lp and g_lp per candidate, row index (b, i, m).
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fwd2_load_row(const float* __restrict__ src, int Dx, bool live, float (&x)[16]);
+
 template <int NPG>
 __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -860,6 +862,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
 
       // ---- candidate x~ = mean + sp * eps  (same arithmetic as ffbsi_step_kernel)
       float x[16];
+      float m1v[16];                                                       // the trajectory's first proposal mean: one 128-bit row read
+      if (!last) tc_fwd2_load_row(a.mu1i + ((size_t)b * N + i) * Dx, Dx, true, m1v);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         float e[4] = {0.f, 0.f, 0.f, 0.f};
@@ -881,7 +885,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
             float mean;
             if (last) mean = rc[d];
             else {
-              const float m1 = __ldg(a.mu1i + ((size_t)b * N + i) * Dx + d), m2 = rc[d];
+              const float m1 = m1v[d], m2 = rc[d];
               mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
             }
             xv = mean + sp[d] * e[k];
@@ -896,7 +900,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
         tc_mlp_compute(g, x, nchunk);
         float muf[16];
         tc::tmem_ld16(g.tb + kColD2, muf);
-        const float* xn = a.X_next + ((bt + 1) * N + i) * Dx;
+        float xn[16];
+        tc_fwd2_load_row(a.X_next + ((bt + 1) * N + i) * Dx, Dx, true, xn);
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
