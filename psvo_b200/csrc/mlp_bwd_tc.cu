@@ -345,10 +345,28 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
         if (a.scatter != nullptr) {
           const int parent = a.scatter[(long long)b * a.scatter_seq_stride + n];
           float* dst = a.gx + ((long long)b * N + parent) * din;
-          for (int d = d0; d < d1; ++d) atomicAdd(dst + d, dx[d] * un);
+          if (din == 16) {                                                 // two 128-bit reductions per thread instead of eight scalar ones
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (half ? dx[8 + k] : dx[k]) * un;
+            atomicAdd(reinterpret_cast<float4*>(dst + d0), make_float4(v[0], v[1], v[2], v[3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + d0 + 4), make_float4(v[4], v[5], v[6], v[7]));
+          } else {
+#pragma unroll
+            for (int d = 0; d < 16; ++d) if (d >= d0 && d < d1) atomicAdd(dst + d, dx[d] * un);     // static indices: dx stays in registers
+          }
         } else {
           float* dst = a.gx + r * din;
-          for (int d = d0; d < d1; ++d) dst[d] = dx[d] * un;
+          if (din == 16) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (half ? dx[8 + k] : dx[k]) * un;
+            reinterpret_cast<float4*>(dst + d0)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(dst + d0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int d = 0; d < 16; ++d) if (d >= d0 && d < d1) dst[d] = dx[d] * un;
+          }
         }
       }
     }

@@ -429,8 +429,10 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
         for (int d = 0; d < PSVO_MAX_DX; ++d) if (d < Dx) { r_mu[d] = p_mu[d]; r_x[d] = p_x[d]; r_gi[d] = p_gi[d]; r_gg[d] = p_gg[d]; }
       }
     }
+    float gm2v[PSVO_MAX_DX];
 #pragma unroll
     for (int d = 0; d < PSVO_MAX_DX; ++d) {
+      gm2v[d] = 0.0f;
       if (d < Dx) {
         float gm2 = 0.0f;
         if (live) {
@@ -452,13 +454,39 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
           const float gv = gX * sp[d] * inv1[d] + gl * zf * inv1[d];        // via m, plus d f_lp / d muf (muf IS mu1)
           a.ext_g[id * Dx + d] = gv; gabs = fmaxf(gabs, fabsf(gv));
         }
-        if (uniform) {
-          const float v = warp_sum(gm2);
-          if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(a.gmu2_all + bt * Dx + d, v);
-        } else if (live && gm2 != 0.0f) {
-          atomicAdd(a.gmu2_all + bt * Dx + d, gm2);
-        }
+        if (uniform) gm2v[d] = gm2;
+        else if (live && gm2 != 0.0f) atomicAdd(a.gmu2_all + bt * Dx + d, gm2);
       }
+    }
+    if (uniform) {
+      // the warp's 16 column sums with 16 shuffles instead of 16 x 5: every butterfly step halves the values a lane carries
+      // (lane bit 4 picks the half, bit 3 the quarter, ...); lanes 2k and 2k+1 end up with the total of column k's bit pattern
+      const int lane = threadIdx.x & 31;
+      float w8[8], w4[4], w2[2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool hi = lane & 16;
+        const float keep = hi ? gm2v[i + 8] : gm2v[i], send = hi ? gm2v[i] : gm2v[i + 8];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool hi = lane & 8;
+        const float keep = hi ? w8[i + 4] : w8[i], send = hi ? w8[i] : w8[i + 4];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool hi = lane & 4;
+        const float keep = hi ? w4[i + 2] : w4[i], send = hi ? w4[i] : w4[i + 2];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      const bool hi = lane & 2;
+      float v = (hi ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, hi ? w2[0] : w2[1], 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const size_t bt0 = (size_t)b0 * a.T + a.t;
+      if ((lane & 1) == 0 && col < Dx && v != 0.0f) atomicAdd(a.gmu2_all + bt0 * Dx + col, v);
     }
   }
   if (a.gmax != nullptr) {
@@ -717,6 +745,8 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   }
   a.ext_mu = nullptr; a.ext_g = nullptr;
   const int light_grid = (int)(((long long)B * N + 255) / 256 < 8LL * num_sms() ? ((long long)B * N + 255) / 256 : 8LL * num_sms());
+  // the proposal kernel ends with 64 warp reductions per thread (sigma statistics): two CTAs per SM, several rows per thread
+  const int prop_grid = light_grid < 2 * num_sms() ? light_grid : 2 * num_sms();
 
   float* gXin = w.gXa;      // children contribution for the current step (zero at t = T-1)
   float* gXout = w.gXb;
@@ -749,7 +779,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
         a.ext_mu = w.tc_muq; a.gmax = w.gmax + 1;
         {
           ProfScope ps_(PK_BWD, st);
-          proposal_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+          proposal_grad_kernel<<<prop_grid, 256, 0, st>>>(a);
           PSVO_LAUNCH_CHECK();
         }
         if ((rc = launch_mlp_bwd_tc(a.q1, w.img_q1, Xp, sstr, w.tc_g, B, N, gXout, anc + (size_t)(t - 1) * N, (long long)T * N,
@@ -782,7 +812,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
         a.ext_mu = w.tc_muq;
         {
           ProfScope ps_(PK_BWD, st);
-          proposal_grad_kernel<<<light_grid, 256, 0, st>>>(a);
+          proposal_grad_kernel<<<prop_grid, 256, 0, st>>>(a);
           PSVO_LAUNCH_CHECK();
         }
         if (int e = launch_mlp_rows_backward(a.q1, w.rows_x, w.tc_g, (int64_t)BN, w.rows_gx, &a.gq1, st)) return e;

@@ -61,6 +61,7 @@ struct ResampleArgs {
 int launch_resample(const ResampleArgs& a, cudaStream_t st);
 
 // persistent whole-filter kernel (one launch per pass, one CTA per sequence): small N / few sequences
+bool persistent_env();     // PSVO_PERSISTENT != 0: whole-filter kernels allowed
 bool persistent_filter_supported(const PropArgs& a, const PropPlan& pl, size_t* smem_out, int* block_out);
 int launch_filter_persistent(PropArgs pa, const ResampleArgs& ra, const PropPlan& pl, cudaStream_t st);
 // cluster whole-filter kernel (one launch per pass, one thread-block cluster per sequence): few sequences of many particles
