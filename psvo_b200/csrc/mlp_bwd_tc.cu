@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
     unsigned char* ph_h = sm + L.hc_hi + half * 4 * kBtGrp + row * 16; unsigned char* ph_l = sm + L.hc_lo + half * 4 * kBtGrp + row * 16;
     unsigned char* pp_h = sm + L.gp_hi + half * 4 * kBtGrp + row * 16; unsigned char* pp_l = sm + L.gp_lo + half * 4 * kBtGrp + row * 16;
     uint32_t n_tile = 0, n_chunk = 0;
+    float db2acc[32];                                  // half 1: this thread's rows' share of db2 = sum over rows of G, reduced once per CTA
+#pragma unroll
+    for (int i = 0; i < 32; ++i) db2acc[i] = 0.0f;
     // every MMA issued for chunks < k complete: the last users of both operand buffers committed
     auto wait_all_mmas = [&](uint32_t k) {
       tc::mbar_wait(a_free + ((k - 1) & 1u), ((k - 1) >> 1) & 1u);
@@ -283,8 +286,7 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
               const int o = kg * 8 + i;
               const float gv = rv[o];
               v[i] = gv * sG;
-              const float s = warp_sum(gv);                                 // db2 = sum over rows of G
-              if (lane == 0 && o < dout && s != 0.0f) atomicAdd(&sdb2[o], s);
+              db2acc[o] += gv;                                              // db2 = sum over rows of G
             }
             uint4 hi, lo;
             tc::split8_f16(v, hi, lo);
@@ -371,6 +373,13 @@ __global__ void __launch_bounds__(352, 1) mlp_bwd_tc_kernel(BtArgs a) {
       }
     }
 
+    if (half == 1) {
+#pragma unroll
+      for (int o = 0; o < 32; ++o) {
+        const float s = warp_sum(db2acc[o]);
+        if (lane == 0 && o < dout && s != 0.0f) atomicAdd(&sdb2[o], s);
+      }
+    }
     // ---- flush the weight-gradient accumulators (all MMAs of this CTA complete)
     if (n_chunk > 0) wait_all_mmas(n_chunk);
     if (n_chunk > 0) {
