@@ -279,17 +279,53 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     __syncthreads();
 
     // ---- per trajectory: normalise over the M candidates, pick one  (PSVO.py:96-104,136-144)
-    if (live && m == 0) {
-      const float* cand = sCand + (size_t)il * M * 5;
+    // M a power of two <= 32: a trajectory's candidates are M consecutive lanes of one warp, and the integer part of the pick
+    // (2 M deterministic exps when one thread does it alone -- with 30 of 32 lanes idle it was 40 % of this kernel) is one exp
+    // per lane, a segmented shuffle scan and a ballot.  Integer sums: the same pick bit for bit.  The floating-point
+    // normaliser keeps its sequential order (every lane evaluates it).
+    const bool seg_pick = a.forced_pick == nullptr && M <= 32 && (M & (M - 1)) == 0;
+    int sel_seg = 0;
+    float lse_seg = 0.0f;
+    if (seg_pick) {
+      const float* cand = sCand + (size_t)il * M * 5;                      // il * M + m = threadIdx.x: always inside the block's array
       float mxo = -INFINITY;
       for (int k = 0; k < M; ++k) mxo = fmaxf(mxo, cand[k * 5]);
       float se = 0.f;
       for (int k = 0; k < M; ++k) se += expf(cand[k * 5] - mxo);
       const float lse_m = mxo + logf(se);
+      const float mxn = mxo - lse_m;
+      lse_seg = lse_m;
+      unsigned long long run = fixed_weight(cand[m * 5] - lse_m, mxn);
+      const int sl = threadIdx.x & (M - 1);
+      for (int o = 1; o < M; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, run, o, M);
+        if (sl >= o) run += up;
+      }
+      const unsigned long long total = __shfl_sync(0xffffffffu, run, M - 1, M);
+      uint32_t u24;
+      if (a.u_pick != nullptr) u24 = u24_from_float(a.u_pick[bt * N + ii]);
+      else u24 = uniform_bits(a.seed, ((uint64_t)(a.seq_offset + b) * T + t) * N + ii, 3u) >> 8;
+      const unsigned long long thr = draw_threshold(total, u24);
+      const unsigned vote = __ballot_sync(0xffffffffu, run <= thr);
+      const unsigned segbits = (vote >> ((threadIdx.x & 31) & ~(M - 1))) & (M == 32 ? 0xffffffffu : ((1u << M) - 1u));
+      sel_seg = __popc(segbits);
+      sel_seg = sel_seg < M ? sel_seg : M - 1;
+    }
+    if (live && m == 0) {
+      const float* cand = sCand + (size_t)il * M * 5;
+      float mxo = -INFINITY, lse_m = lse_seg;
+      if (!seg_pick) {
+        for (int k = 0; k < M; ++k) mxo = fmaxf(mxo, cand[k * 5]);
+        float se = 0.f;
+        for (int k = 0; k < M; ++k) se += expf(cand[k * 5] - mxo);
+        lse_m = mxo + logf(se);
+      }
       // normalised log omega; its maximum is mxo - lse_m
       const float mxn = mxo - lse_m;
       int sel;
-      if (a.forced_pick != nullptr) {
+      if (seg_pick) {
+        sel = sel_seg;
+      } else if (a.forced_pick != nullptr) {
         sel = a.forced_pick[bt * N + i];
         sel = sel < 0 ? 0 : (sel >= M ? M - 1 : sel);
       } else {
