@@ -59,6 +59,12 @@ template <int DXP>
 static int launch_particle_mlp(const psvo_mlp& net, const float* in, long long seq_stride, int B, int N, int Dx,
                                float* out, cudaStream_t st) {
   PSVO_REQUIRE(net.n_hidden <= 1, "psvo_ffbsi: per-particle networks with more than one hidden layer are not supported yet");
+  {
+    // many rows through a wide hidden layer: the tcgen05 row MLP (tc_mlp.cu; fp16x3 split, 1e-5 like the other tensor-core paths)
+    static const bool tc_off = getenv("PSVO_DISABLE_TC") != nullptr && getenv("PSVO_DISABLE_TC")[0] == '1';
+    if (!tc_off && (long long)B * N >= 16384 && net.n_hidden == 1 && net.width[0] >= 128 && net.d_out == Dx && tc_mlp_supported(net))
+      return launch_particle_mlp_tc(net, in, seq_stride, B, N, out, st);
+  }
   const size_t smem = staged_bytes(net, DXP, DXP);
   auto kern = particle_mlp_kernel<DXP, DXP>;
   PSVO_DYN_SMEM(kern, smem);
