@@ -25,11 +25,15 @@ __host__ __device__ inline int rg_chunk_shift(int n, int nt = kRgThreads) {
   while ((1 << s) < cl) ++s;
   return s;
 }
+// guide slices per particle (a power of two): more slices = narrower brackets for the inverse-CDF search, a longer table to build
+#ifndef PSVO_GUIDE_FACTOR
+#define PSVO_GUIDE_FACTOR 1
+#endif
 __host__ __device__ inline int rg_guide_bits(int N, int nt = kRgThreads) {
   int kbits = 0;
   while ((1 << kbits) < nt) ++kbits;                 // K >= nt: one guide slice per thread at least
-  while ((1 << kbits) < N) ++kbits;
-  return kbits;
+  while ((1 << kbits) < N * PSVO_GUIDE_FACTOR) ++kbits;
+  return kbits < 24 ? kbits : 24;
 }
 // bytes of the region: [lock + flags + cross-warp scratch: 1 KB] | CDF (u64) | log weights (f32) | guide table (i32)
 __host__ __device__ inline size_t rg_smem_bytes(int N, int nt = kRgThreads) {
