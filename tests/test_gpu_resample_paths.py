@@ -107,8 +107,8 @@ CLUSTER_CASES = [(4, 1, [64], 2048, 1, 6, True, True),        # BASELINE config 
 def test_cluster_filter_kernel_is_bit_identical_to_per_step_launches(tmp_path):
     """smc_filter_cluster_kernel (one thread-block cluster per sequence, one cluster barrier per time step) against the
     per-step launches of the same device code (PSVO_CLUSTER=0 in a subprocess)."""
-    if os.environ.get("PSVO_CLUSTER") == "0":
-        pytest.skip("inside the per-step re-run")
+    if os.environ.get("PSVO_CLUSTER") == "0" or os.environ.get("PSVO_PERSISTENT") == "0":
+        pytest.skip("whole-filter kernels switched off in this process")
     got = [_run_cfg(*c) for c in CLUSTER_CASES]
     dump = str(tmp_path / "perstep.pt")
     code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_resample_paths as m; "
