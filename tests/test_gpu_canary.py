@@ -77,6 +77,8 @@ CASES = [
     ("ragged_per_step", 5, 7, [24], 2500, 5, 3, 3, True),
     ("tc_paths", 13, 29, [128], 4100, 4, 5, 3, False),
     ("linear", 4, 4, [], 1030, 2, 2, 3, False),
+    ("tc_thread_contiguous_resample", 16, 32, [128], 4096, 4, 80, 2, False),   # one resampling CTA per sequence: smc_resample_lean_kernel
+    ("psvo_whole_pass", 2, 1, [16], 16, 16, 1, 6, False),                      # batch 1: the backward simulation is one launch; sliced pair kernel in reverse
 ]
 
 
