@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) emission_grad_kernel(BwdArgs a) {
 }
 
 // t >= 1, f aliases d1 = q1:  mu1 = MLP q1(X_anc[t-1]) from ext_mu; writes d/dmu1 to ext_g
-__global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(256, 1) proposal_grad_kernel(BwdArgs a) {
   __shared__ float sstat[4 * 32];
   __shared__ float sp[PSVO_MAX_DX], inv1[PSVO_MAX_DX], inv2[PSVO_MAX_DX];
   const int Dx = a.Dx, N = a.N;
@@ -429,16 +429,31 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
         for (int d = 0; d < PSVO_MAX_DX; ++d) if (d < Dx) { r_mu[d] = p_mu[d]; r_x[d] = p_x[d]; r_gi[d] = p_gi[d]; r_gg[d] = p_gg[d]; }
       }
     }
-    float gm2v[PSVO_MAX_DX];
+    float gm2v[PSVO_MAX_DX], gout[PSVO_MAX_DX], r_m2[PSVO_MAX_DX];
+    {
+      const float* p_m2 = a.mu2_all + bt * Dx;                           // the sequence's second proposal mean: one 128-bit row read
+      if ((Dx & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < PSVO_MAX_DX / 4; ++q) {
+          if (4 * q < Dx) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p_m2) + q);
+            r_m2[4 * q] = v.x; r_m2[4 * q + 1] = v.y; r_m2[4 * q + 2] = v.z; r_m2[4 * q + 3] = v.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < PSVO_MAX_DX; ++d) if (d < Dx) r_m2[d] = __ldg(p_m2 + d);
+      }
+    }
 #pragma unroll
     for (int d = 0; d < PSVO_MAX_DX; ++d) {
-      gm2v[d] = 0.0f;
+      gm2v[d] = 0.0f; gout[d] = 0.0f;
       if (d < Dx) {
         float gm2 = 0.0f;
         if (live) {
           const float mu1 = r_mu[d];
           const float X = r_x[d];
-          const float m2 = __ldg(a.mu2_all + bt * Dx + d);
+          const float m2 = r_m2[d];
           const float A = inv1[d] * mu1 + inv2[d] * m2;                   // m / sp
           const float m = sp[d] * A;
           const float isp = inv1[d] + inv2[d];                            // 1 / sp
@@ -452,10 +467,21 @@ __global__ void __launch_bounds__(256, 2) proposal_grad_kernel(BwdArgs a) {
           st_i2[d] += gX * sp[d] * m2;
           gm2 = gX * sp[d] * inv2[d];
           const float gv = gX * sp[d] * inv1[d] + gl * zf * inv1[d];        // via m, plus d f_lp / d muf (muf IS mu1)
-          a.ext_g[id * Dx + d] = gv; gabs = fmaxf(gabs, fabsf(gv));
+          gout[d] = gv; gabs = fmaxf(gabs, fabsf(gv));
         }
         if (uniform) gm2v[d] = gm2;
         else if (live && gm2 != 0.0f) atomicAdd(a.gmu2_all + bt * Dx + d, gm2);
+      }
+    }
+    if (live) {                                                            // the row of upstream gradients: 128-bit stores
+      float* p_g = a.ext_g + id * Dx;
+      if ((Dx & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < PSVO_MAX_DX / 4; ++q)
+          if (4 * q < Dx) reinterpret_cast<float4*>(p_g)[q] = make_float4(gout[4 * q], gout[4 * q + 1], gout[4 * q + 2], gout[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < PSVO_MAX_DX; ++d) if (d < Dx) p_g[d] = gout[d];
       }
     }
     if (uniform) {
@@ -746,7 +772,7 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
   a.ext_mu = nullptr; a.ext_g = nullptr;
   const int light_grid = (int)(((long long)B * N + 255) / 256 < 8LL * num_sms() ? ((long long)B * N + 255) / 256 : 8LL * num_sms());
   // the proposal kernel ends with 64 warp reductions per thread (sigma statistics): two CTAs per SM, several rows per thread
-  const int prop_grid = light_grid < 2 * num_sms() ? light_grid : 2 * num_sms();
+  const int prop_grid = light_grid < num_sms() ? light_grid : num_sms();
 
   float* gXin = w.gXa;      // children contribution for the current step (zero at t = T-1)
   float* gXout = w.gXb;
