@@ -7,18 +7,20 @@
 // Shape of the work (BASELINE config 5: Dx=16, Dy=32, H=256): per particle-step 41 kFLOP of tiny-K GEMMs
 //   [128 x 16] x [16 x 256] -> relu -> [128 x 256] x [256 x 16|32].
 //
-// CTA = 4 compute groups of 128 threads + 4 MMA-issuing warps (one per group).  A group owns one 128-particle tile
-// at a time (TMEM lane == row == thread) and walks the hidden layer of each network in chunks of 32 units:
-//     compute threads : wait L1(c) -> tcgen05.ld the D1 row -> scale + bias -> ReLU -> fp16 hi/lo split (registers)
-//                       -> wait L2(c-1) -> 16-byte stores into the A2 operand -> fence.proxy.async ->
-//                       mbarrier.arrive full[g]          (no block- or group-wide barrier in the loop)
-//     MMA warp g      : wait full[g] -> L2(c) (2 K-steps x 2 MMAs) -> commit ; L1(c+2) (3 MMAs) -> commit
-// D1 is double buffered in TMEM so L1 runs two chunks ahead of the epilogue, and the wait for L2(c-1) sits after the
-// register work of chunk c, so the compute warps only ever stall when the tensor pipe is the bottleneck.
-// Measured cost model (profiles/microbench): a K=16 tcgen05.mma occupies the tensor pipe for max(40, N/2) cycles
-// whatever its size, so MMAs are made as wide as TMEM allows: the layer-2 weights are stacked [w_hi ; w_lo] along N,
-// which turns hi*hi + hi*lo into ONE instruction (the two halves of the accumulator are added in the epilogue).
-// All groups share the staged fp16 weights (80 KB at H = 256).
+// CTA = 4 compute groups of 128 threads + 4 MMA-issuing warps (one per group).  A group owns one 128-particle tile at a time
+// (TMEM lane == row == thread) and walks the hidden layer of each network in stages of 16 units (one K-step of layer 2):
+//     MMA warp g      : L1 of stage c (4 TS-form MMAs, N = 16: x_hi W_hi + x_hi W_lo + x_lo W_hi + bias) into one of FOUR layer-1
+//                       accumulators, four stages ahead of the conversion; when stage c has been converted: L2 of stage c (3 MMAs,
+//                       A operand = the converted accumulator itself) and L1 of stage c+4 into the very same columns
+//     compute threads : wait L1(c) -> tcgen05.ld the accumulator row (prefetched one stage early) -> ReLU + fp16 hi/lo split in
+//                       registers -> tcgen05.st the pair back IN PLACE -> mbarrier.arrive (published one stage late: no exposed
+//                       wait::st).  The activations never touch shared memory; there is no block- or group-wide barrier in the loop.
+// Every MMA is in TS form (A operand in tensor memory: the network's input row, the `ones` operand of the bias MMA, the
+// converted activations), which costs N/2 + 1 pipe cycles down to N = 16 (profiles/microbench/r2_pipe_bench.cu); with the A
+// operand in shared memory the floor is 32 + N/4 cycles (the 4 KB A tile at 128 B/clk).  All groups share the staged fp16
+// weights (~96 KB at H = 256), copied by cp.async.bulk once per launch; DESIGN.md section 4a has the measurements.
+// The same body (tc_prop_body) is the per-step kernel and the opt-in persistent whole-filter kernel (per-sequence flags in
+// global memory instead of kernel boundaries, resampling inside the kernel: DESIGN.md section 4b).
 // Arithmetic ("fp16x3"): x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 mantissa bits); a*w is evaluated as
 // a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation in TMEM; weights are pre-scaled by 2^8 (exact) so that
 // their lo halves stay in fp16's normal range, and the scale is undone inside the bias FFMA.  Operands must stay
