@@ -85,6 +85,7 @@ bool cluster_filter_supported(const PropArgs& a, int* csize_out, int* block_out,
   if (a.q1.n_hidden > 1 || a.g.n_hidden > 1 || (sep_f && a.f.n_hidden > 1)) return false;
   if (a.T < 2 || a.N < 512 || a.N > 8192) return false;
   int csize = 8;
+  if (const char* e = getenv("PSVO_CLUSTER_SIZE")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) csize = v; }   // experiment hook
   while (csize > 1 && (a.N / csize < 128 || (long long)a.B * csize > num_sms())) csize /= 2;
   if (csize < 2) return false;
   const int chunk = (a.N + csize - 1) / csize;
