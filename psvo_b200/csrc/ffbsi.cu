@@ -99,6 +99,7 @@ struct FfbsiArgs {
   float* bw_Xs; int* pick; float* out_f; float* out_g; float* out_a; float* omega_pick; float* omega_all;
   const float* P_ext;        // (B,N,M) pairwise log-sum-exp from the tensor-core kernel, or NULL -> SIMT loop below
   const float* F_ext; const float* G_ext;   // (B,N,M) f_lp / g_lp of every candidate from ffbsi_cand_tc_kernel, or NULL
+  const float* Q_ext = nullptr;             // (B,N,M) proposal log-density of every candidate from the same kernel, or NULL
   unsigned long long seed;
   int N, M, B, T, Dx, Dy, t, seq_offset, IL;
   unsigned flags;
@@ -174,9 +175,18 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     const size_t bt = (size_t)b * T + t;
     const int ii = live ? i : 0;
 
+    // With every term of omega precomputed on the tensor cores (f, g, q per candidate from ffbsi_cand_tc_kernel, the pairwise
+    // term from ffbsi_pair_tc_kernel) this kernel does not need the candidates themselves: only the PICKED one is materialised,
+    // after the pick, four dimensions per lane (one Philox block per lane instead of four per candidate)
+    const bool lean = ext && a.Q_ext != nullptr && a.P_ext != nullptr && !first && a.mu1i_next == nullptr &&
+                      a.forced_pick == nullptr && M >= 4 && M <= 32 && (M & (M - 1)) == 0;
     // ---- proposal sample
     float X[1][DXP], xn[DXP];
     float qs = 0.f;
+    if (lean) {
+#pragma unroll
+      for (int d = 0; d < DXP; ++d) { X[0][d] = 0.0f; xn[d] = 0.0f; }
+    } else
 #pragma unroll
     for (int c = 0; c < DXP / 4; ++c) {
       float e[4] = {0.f, 0.f, 0.f, 0.f};
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
         X[0][d] = xv; xn[d] = xnext;
       }
     }
-    const float q_lp = -0.5f * qs - lds[0] - cx;
+    const float q_lp = lean ? a.Q_ext[((size_t)b * N + ii) * M + (live ? m : 0)] : -0.5f * qs - lds[0] - cx;
 
     // ---- f(x_{t+1} | x~)  (MLP f on the candidate)
     float f_lp = 0.0f;
@@ -280,8 +290,10 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
     __syncthreads();
     sCand[threadIdx.x * 5 + 0] = omega; sCand[threadIdx.x * 5 + 1] = f_lp; sCand[threadIdx.x * 5 + 2] = g_lp;
     sCand[threadIdx.x * 5 + 3] = q_lp;  sCand[threadIdx.x * 5 + 4] = P;
+    if (!lean) {
 #pragma unroll
-    for (int d = 0; d < DXP; ++d) sX[threadIdx.x * DXP + d] = X[0][d];
+      for (int d = 0; d < DXP; ++d) sX[threadIdx.x * DXP + d] = X[0][d];
+    }
     __syncthreads();
 
     // ---- per trajectory: normalise over the M candidates, pick one  (PSVO.py:96-104,136-144)
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
       const float* c = cand + sel * 5;
       const float om = c[0] - lse_m, fl = c[1], gl = c[2], ql = c[3], Pl = c[4];
       const float* xsel = sX + ((size_t)il * M + sel) * DXP;
-      for (int d = 0; d < Dx; ++d) a.bw_Xs[(bt * N + i) * Dx + d] = xsel[d];
+      if (!lean) for (int d = 0; d < Dx; ++d) a.bw_Xs[(bt * N + i) * Dx + d] = xsel[d];
       a.pick[bt * N + i] = sel;
       if (fuse_q1i) {                                                             // mu1i of step t-1 = MLP q1_inv(bw_X_t) (PSVO.py:120)
         float xin[1][DXP], mo[1][DXP];
@@ -368,6 +380,33 @@ __global__ void __launch_bounds__(256) ffbsi_step_kernel(FfbsiArgs a) {
       } else {
         a.out_a[bt * N + i] = last ? ((((Pl + gl) - ql) - om) - logM) : ((Pl + gl) - ((ql + om) + logM));   // bw_log_W
         a.omega_pick[bt * N + i] = om;
+      }
+    }
+    if (lean && live && 4 * m < Dx) {
+      // the picked candidate x~[sel, i] = mean + sp * eps, dimensions [4 m, 4 m + 4) by lane m of the trajectory (same arithmetic
+      // as ffbsi_cand_tc_kernel used for its densities)
+      const int sel = sel_seg;
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.eps_bw != nullptr) {
+        const float* src = a.eps_bw + (((bt * M + sel) * N + i) * (size_t)Dx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (4 * m + k < Dx) e[k] = src[4 * m + k];
+      } else {
+        const uint64_t gidx = ((((uint64_t)(a.seq_offset + b) * T + t) * M + sel) * N) + i;
+        normal4(philox4x32_10(a.seed, gidx, (uint32_t)m, 2u), e);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = 4 * m + k;
+        if (d < Dx) {
+          float mean;
+          if (last) mean = a.mu_init_all[bt * Dx + d];
+          else {
+            const float m1 = a.mu1i[((size_t)b * N + i) * Dx + d], m2 = a.m2_all[bt * Dx + d];
+            mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
+          }
+          a.bw_Xs[(bt * N + i) * Dx + d] = mean + sp[d] * e[k];
+        }
       }
     }
   }
@@ -422,7 +461,7 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG; unsigned char *bimg, *tc_image; size_t bytes; };
+struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG, *candQ; unsigned char *bimg, *tc_image; size_t bytes; };
 static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
@@ -439,11 +478,11 @@ static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
     w.candP = take(BN * d->M);
     w.bimg = reinterpret_cast<unsigned char*>(take(ffbsi_pair_tc_image_bytes(d->B, d->N) / sizeof(float)));
   }
-  w.candF = w.candG = nullptr; w.tc_image = nullptr;
+  w.candF = w.candG = w.candQ = nullptr; w.tc_image = nullptr;
   if (p != nullptr) {
     const psvo_mlp& fnet = (d->flags & PSVO_F_BOOTSTRAP) ? p->q1.net : p->f.net;
     if (ffbsi_cand_tc_supported(fnet, p->g.net, d->Dx, d->Dy, (long long)BN * d->M)) {
-      w.candF = take(BN * d->M); w.candG = take(BN * d->M);
+      w.candF = take(BN * d->M); w.candG = take(BN * d->M); w.candQ = take(BN * d->M);
       w.tc_image = reinterpret_cast<unsigned char*>(take(32 * 1024));
     }
   }
@@ -524,10 +563,10 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
     ia.q1 = fd.net; ia.f = fd.net; ia.g = p->g.net; ia.Dx = Dx; ia.Dy = d->Dy;
     if (int e = launch_tc_stage_image(ia, w.tc_image, st)) return e;
     ca.tc_image = w.tc_image; ca.sig = w.sig; ca.obs = obs; ca.mu1i = w.mu1i; ca.m2_all = w.m2_all; ca.mu_init_all = w.mu_init_all;
-    ca.X_next = a.X_next; ca.eps_bw = eps_bw; ca.candF = w.candF; ca.candG = w.candG; ca.seed = seed;
+    ca.X_next = a.X_next; ca.eps_bw = eps_bw; ca.candF = w.candF; ca.candG = w.candG; ca.candQ = w.candQ; ca.seed = seed;
     ca.N = N; ca.M = M; ca.B = B; ca.T = T; ca.Dx = Dx; ca.Dy = d->Dy; ca.H = p->g.net.width[0]; ca.seq_offset = d->seq_offset;
     ca.flags = d->flags;
-    a.F_ext = w.candF; a.G_ext = w.candG;
+    a.F_ext = w.candF; a.G_ext = w.candG; a.Q_ext = w.candQ;
   }
 
   const int DXP = pad_dx(Dx), DYP = pad_dy(d->Dy);

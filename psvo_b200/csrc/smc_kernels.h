@@ -118,6 +118,7 @@ struct CandTcArgs {
   const unsigned char* tc_image; const float* sig; const float* obs;
   const float* mu1i; const float* m2_all; const float* mu_init_all; const float* X_next; const float* eps_bw;
   float* candF; float* candG;        // (B, N, M) out: f_lp (0 at t = T-1) and g_lp of every candidate
+  float* candQ = nullptr;            // (B, N, M) out (optional): proposal log-density q(x~) of every candidate
   unsigned long long seed;
   int N, M, B, T, Dx, Dy, H, t, seq_offset;
   unsigned flags;

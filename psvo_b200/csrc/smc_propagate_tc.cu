@@ -816,10 +816,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
   TcCtx tcx;
   tc_setup_finish<NPG>(sm, L, H, tcx);
   if (tid == 0) {
-    float lf = 0.f, lg = 0.f;
-    for (int d = 0; d < Dx; ++d) lf += logf(a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d]);
+    float lf = 0.f, lg = 0.f, lq = 0.f;
+    for (int d = 0; d < Dx; ++d) { lf += logf(a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d]); lq += logf(C[d]); }
     if (!poisson) for (int d = 0; d < Dy; ++d) lg += logf(a.sig[SIG_G * 32 + d]);
-    C[96] = lf; C[97] = lg;
+    C[96] = lf; C[97] = lg; C[98] = lq;
   }
   __syncthreads();
   const long long ncand = (long long)N * M;
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     const int grp = warp >> 2;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
     const float* inv_sg = C + 64;
-    const float ld_f = C[96], ld_g = C[97];
+    const float ld_f = C[96], ld_g = C[97], ld_q = C[98];
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     TcGroup g;
     const int gt = tid & 127;
@@ -864,6 +864,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
 
       // ---- candidate x~ = mean + sp * eps  (same arithmetic as ffbsi_step_kernel)
       float x[16];
+      float qs = 0.f;
       float m1v[16];                                                       // the trajectory's first proposal mean: one 128-bit row read
       if (!last) tc_fwd2_load_row(a.mu1i + ((size_t)b * N + i) * Dx, Dx, true, m1v);
 #pragma unroll
@@ -891,6 +892,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
               mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
             }
             xv = mean + sp[d] * e[k];
+            const float z = (xv - mean) / sp[d];                              // the proposal density, as ffbsi_step_kernel evaluates it
+            qs = fmaf(z, z, qs);
           }
           x[d] = xv;
         }
@@ -946,6 +949,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
       if (live) {
         a.candF[(size_t)b * ncand + c] = f_lp;
         a.candG[(size_t)b * ncand + c] = g_lp;
+        if (a.candQ != nullptr) a.candQ[(size_t)b * ncand + c] = -0.5f * qs - ld_q - cx;
       }
     }
   }
