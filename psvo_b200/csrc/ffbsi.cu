@@ -461,7 +461,7 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG, *candQ; unsigned char *bimg, *tc_image; size_t bytes; };
+struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG, *candQ; unsigned char *bimg, *tc_image, *tc_image2; size_t bytes; };
 static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
@@ -478,12 +478,13 @@ static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
     w.candP = take(BN * d->M);
     w.bimg = reinterpret_cast<unsigned char*>(take(ffbsi_pair_tc_image_bytes(d->B, d->N) / sizeof(float)));
   }
-  w.candF = w.candG = w.candQ = nullptr; w.tc_image = nullptr;
+  w.candF = w.candG = w.candQ = nullptr; w.tc_image = w.tc_image2 = nullptr;
   if (p != nullptr) {
     const psvo_mlp& fnet = (d->flags & PSVO_F_BOOTSTRAP) ? p->q1.net : p->f.net;
     if (ffbsi_cand_tc_supported(fnet, p->g.net, d->Dx, d->Dy, (long long)BN * d->M)) {
       w.candF = take(BN * d->M); w.candG = take(BN * d->M); w.candQ = take(BN * d->M);
       w.tc_image = reinterpret_cast<unsigned char*>(take(32 * 1024));
+      w.tc_image2 = reinterpret_cast<unsigned char*>(take(32 * 1024));      // q1_inv in the "q" slot: the row MLPs of the time loop
     }
   }
   w.bytes = off;
@@ -557,11 +558,18 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   // candidate MLPs f and g on tensor cores (one fp16 weight image per pass, f in the "q" slot)
   a.F_ext = nullptr; a.G_ext = nullptr;
   const bool cand_tc = w.candF != nullptr;
+  bool rows_tc = false;      // the two row MLPs of a step (transition means, inverse-proposal means) on the tcgen05 pipeline too
   CandTcArgs ca;
   if (cand_tc) {
     PropArgs ia;
     ia.q1 = fd.net; ia.f = fd.net; ia.g = p->g.net; ia.Dx = Dx; ia.Dy = d->Dy;
     if (int e = launch_tc_stage_image(ia, w.tc_image, st)) return e;
+    if (tc_pipeline_supported(p->q1_inv.net, p->g.net, Dx, d->Dy)) {
+      PropArgs ib = ia;
+      ib.q1 = p->q1_inv.net; ib.f = p->q1_inv.net;
+      if (int e = launch_tc_stage_image(ib, w.tc_image2, st)) return e;
+      rows_tc = true;
+    }
     ca.tc_image = w.tc_image; ca.sig = w.sig; ca.obs = obs; ca.mu1i = w.mu1i; ca.m2_all = w.m2_all; ca.mu_init_all = w.mu_init_all;
     ca.X_next = a.X_next; ca.eps_bw = eps_bw; ca.candF = w.candF; ca.candG = w.candG; ca.candQ = w.candQ; ca.seed = seed;
     ca.N = N; ca.M = M; ca.B = B; ca.T = T; ca.Dx = Dx; ca.Dy = d->Dy; ca.H = p->g.net.width[0]; ca.seq_offset = d->seq_offset;
@@ -616,6 +624,11 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
     int rc = 0;
     if (t >= 1 && w.mu_f_all != nullptr) {
       a.mu_f = pt.mu_f = w.mu_f_all + (size_t)(t - 1) * N * Dx;
+    } else if (t >= 1 && rows_tc) {
+      Fwd2TcArgs fa;
+      fa.tc_image = w.tc_image; fa.xq = Xs + (size_t)(t - 1) * N * Dx; fa.xg = nullptr; fa.x_seq_stride = (long long)T * N * Dx;
+      fa.muq = w.mu_f; fa.mug = nullptr; fa.B = B; fa.N = N; fa.Dx = Dx; fa.Dy = d->Dy; fa.H = p->g.net.width[0]; fa.prof_kind = PK_FFBSI;
+      if ((rc = launch_tc_fwd2(fa, st))) return rc;
     } else if (t >= 1) {      // mu_f = MLP_f(Xs[t-1])
       const float* in = Xs + (size_t)(t - 1) * N * Dx;
       rc = DXP == 4 ? launch_particle_mlp<4>(fd.net, in, (long long)T * N * Dx, B, N, Dx, w.mu_f, st)
@@ -623,7 +636,12 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
                                 : launch_particle_mlp<16>(fd.net, in, (long long)T * N * Dx, B, N, Dx, w.mu_f, st));
       if (rc) return rc;
     }
-    if (t <= T - 2 && !fuse_q1i) {  // mu1i = MLP_q1_inv(X_{t+1}^{bw})
+    if (t <= T - 2 && !fuse_q1i && rows_tc) {
+      Fwd2TcArgs fa;
+      fa.tc_image = w.tc_image2; fa.xq = a.X_next + (size_t)(t + 1) * N * Dx; fa.xg = nullptr; fa.x_seq_stride = (long long)T * N * Dx;
+      fa.muq = w.mu1i; fa.mug = nullptr; fa.B = B; fa.N = N; fa.Dx = Dx; fa.Dy = d->Dy; fa.H = p->g.net.width[0]; fa.prof_kind = PK_FFBSI;
+      if ((rc = launch_tc_fwd2(fa, st))) return rc;
+    } else if (t <= T - 2 && !fuse_q1i) {  // mu1i = MLP_q1_inv(X_{t+1}^{bw})
       const float* in = a.X_next + (size_t)(t + 1) * N * Dx;
       rc = DXP == 4 ? launch_particle_mlp<4>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)
                     : (DXP == 8 ? launch_particle_mlp<8>(p->q1_inv.net, in, (long long)T * N * Dx, B, N, Dx, w.mu1i, st)

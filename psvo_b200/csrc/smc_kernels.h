@@ -133,8 +133,9 @@ struct Fwd2TcArgs {
   const float* xq; const float* xg; long long x_seq_stride;     // row (b, n) at x + b*stride + n*Dx; xq may be NULL
   float* muq; float* mug;                                       // (B*N, Dx) and (B*N, Dy)
   int B, N, Dx, Dy, H;
+  int prof_kind = PK_BWD;                                       // which profile counter the launch goes to
 };
-int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st);
+int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st);     // xg == NULL: only the network in the "q" slot (xq -> muq)
 bool tc_pipeline_supported(const psvo_mlp& q, const psvo_mlp& g, int Dx, int Dy);
 
 // tensor-core (tcgen05) reverse mode of a one-hidden-layer MLP over particle rows (mlp_bwd_tc.cu)

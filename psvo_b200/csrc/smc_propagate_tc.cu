@@ -342,7 +342,7 @@ __device__ __forceinline__ void tc_mma_net(const TcNetAddr& na, uint32_t lbo1, u
 // the persistent whole-filter kernel hands tiles out dynamically and tells this warp per tile what to run (see below)
 template <int NPG, bool PERSIST = false>
 __device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, const TcPropSmem& L, int H, int grp, int items, int nst, int first_net,
-                                            int work = 0) {
+                                            int work = 0, bool skip_g = false) {
   const uint32_t bars = tc_opaque(sm_base + L.bars + 8u * kTcBars * grp);
   const uint32_t tb = tc_opaque(tmem + grp * 128);
   const uint32_t lbo1 = tc_opaque((uint32_t)H * 16u);
@@ -372,7 +372,7 @@ __device__ __forceinline__ void tc_mma_warp(uint32_t tmem, uint32_t sm_base, con
   } else {
     for (int wi = blockIdx.x * kTcGroups + grp; wi < items; wi += gridDim.x * kTcGroups) {
       if (first_net == 0) tc_mma_net<16>(aq, lbo1, tb, bars, nst, par);
-      tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
+      if (!skip_g) tc_mma_net<NPG>(ag, lbo1, tb, bars, nst, par);
     }
   }
 }
@@ -810,6 +810,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     const float s1 = a.sig[(last ? SIG_BQI : SIG_Q1I) * 32 + d], s2 = a.sig[SIG_BQ2 * 32 + d];
     C[16 + d] = 1.0f / s1; C[32 + d] = 1.0f / s2;
     C[d] = last ? s1 : 1.0f / (1.0f / s1 + 1.0f / s2);
+    C[100 + d] = 1.0f / C[d];
     C[48 + d] = 1.0f / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
   }
   if (tid >= 32 && tid < 64) C[64 + tid - 32] = tid - 32 < Dy ? 1.0f / a.sig[SIG_G * 32 + tid - 32] : 0.0f;   // 0 beyond Dy: padded columns drop out
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     const int grp = warp >> 2;
     const float* sp = C; const float* inv1 = C + 16; const float* inv2 = C + 32; const float* inv_sf = C + 48;
-    const float* inv_sg = C + 64;
+    const float* inv_sg = C + 64; const float* inv_sp = C + 100;
     const float ld_f = C[96], ld_g = C[97], ld_q = C[98];
     const float cx = 0.5f * (float)Dx * kLog2Pi, cy = 0.5f * (float)Dy * kLog2Pi;
     TcGroup g;
@@ -892,7 +893,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ffbsi_cand_tc_kernel(CandTcArgs
               mean = sp[d] * (inv1[d] * m1 + inv2[d] * m2);
             }
             xv = mean + sp[d] * e[k];
-            const float z = (xv - mean) / sp[d];                              // the proposal density, as ffbsi_step_kernel evaluates it
+            const float z = (xv - mean) * inv_sp[d];                          // the proposal density of the candidate
             qs = fmaf(z, z, qs);
           }
           x[d] = xv;
@@ -1008,7 +1009,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
 
   if (warp >= kTcGroups * 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
-    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1);
+    tc_mma_warp<NPG>(tcx.tmem, tc::smem_u32(sm), L, H, warp - kTcGroups * 4, work, nchunk, with_q ? 0 : 1, 0, a.xg == nullptr);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
     const int grp = warp >> 2;
@@ -1028,7 +1029,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
         tc::tmem_ld16(g.tb + kColD2, mu);
         if (live) tc_fwd2_store_row(a.muq + r * Dx, Dx, 0, mu, sb2q);
       }
-      {
+      if (a.xg != nullptr) {
         const float* src = a.xg + (long long)b * a.x_seq_stride + (long long)n * Dx;
         tc_fwd2_load_row(src, Dx, live, x);
         tc_mlp_compute(g, x, nchunk);
@@ -1047,7 +1048,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fwd2_kernel(Fwd2TcArgs a) {
 }
 
 int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st) {
-  PSVO_REQUIRE(a.tc_image != nullptr && a.xg != nullptr && a.mug != nullptr, "tensor-core forward: null buffer");
+  PSVO_REQUIRE(a.tc_image != nullptr && ((a.xg != nullptr && a.mug != nullptr) || (a.xq != nullptr && a.muq != nullptr)), "tensor-core forward: null buffer");
   const TcPropSmem L = tc_prop_layout(a.H, 32);
   const size_t smem = L.total + 128;
   PSVO_REQUIRE(smem <= 227 * 1024, "tensor-core forward: %zu B of shared memory", smem);
@@ -1055,7 +1056,7 @@ int launch_tc_fwd2(const Fwd2TcArgs& a, cudaStream_t st) {
   long long grid = (tiles + kTcGroups - 1) / kTcGroups;
   if (grid > num_sms()) grid = num_sms();
   PSVO_DYN_SMEM(tc_fwd2_kernel<32>, 227 * 1024);
-  ProfScope ps_(PK_BWD, st);
+  ProfScope ps_(a.prof_kind, st);
   tc_fwd2_kernel<32><<<(int)grid, kTcThreads, smem, st>>>(a);
   PSVO_LAUNCH_CHECK();
   return 0;
