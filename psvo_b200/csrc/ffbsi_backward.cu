@@ -644,6 +644,7 @@ static int launch_fb(K kern, const FbArgs& a, int grid, int block, size_t smem, 
 }
 
 struct FbWs {
+  float *mu_f_all, *mu1i_all;      // batch 1: the means of ALL time steps, two launches per pass instead of two per step (or NULL)
   float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *coef, *candX, *candK, *candP, *gmu1i, *gxn, *ginA, *ginB,
         *gm2_all, *gmu_init_all, *gmu0, *stats, *gfeat_tmp, *gx0_tmp;
   size_t bytes;
@@ -656,6 +657,9 @@ static FbWs carve_fb(const psvo_dims* d, char* base) {
   const bool wr = d->flags & PSVO_F_WITH_RESAMPLING;
   w.sig = take(SIG_SLOTS * 32);
   w.mu_f = take(BN * d->Dx); w.mu1i = take(BN * d->Dx);
+  const bool all_steps = d->B == 1 && (size_t)d->T * d->N * d->Dx <= (size_t)1 << 26;
+  w.mu_f_all = all_steps ? take((size_t)d->T * d->N * d->Dx) : nullptr;
+  w.mu1i_all = all_steps ? take((size_t)d->T * d->N * d->Dx) : nullptr;
   w.m2_all = take(BT * d->Dx); w.mu_init_all = take(BT * d->Dx); w.mu0i = take((size_t)d->B * d->Dx);
   w.coef = take(wr ? BT * d->N : BN);
   w.candX = take(BNM * DXP); w.candK = take(BNM); w.candP = take(BNM);
@@ -789,8 +793,19 @@ PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p, const
   for (int t = 0; t < T; ++t) {
     a.t = t; a.gin = gin; a.gin_next = gin_next;
     int rc = 0;
-    if (t >= 1) if ((rc = launch_particle_mlp_dx(fd.net, Xs + (size_t)(t - 1) * N * Dx, (long long)T * N * Dx, B, N, Dx, w.mu_f, st))) return rc;
-    if (t <= T - 2) if ((rc = launch_particle_mlp_dx(p->q1_inv.net, a.X_next + (size_t)(t + 1) * N * Dx, (long long)T * N * Dx, B, N, Dx, w.mu1i, st))) return rc;
+    if (w.mu_f_all != nullptr) {
+      // batch 1: both inputs (the filter's particles, the simulated trajectories) are known for every step: row (t, n) of the
+      // input -> row (t, n) of the all-steps arrays, computed once before the loop ("sequences" = time steps)
+      if (t == 0) {
+        if ((rc = launch_particle_mlp_dx(fd.net, Xs, (long long)N * Dx, T, N, Dx, w.mu_f_all, st))) return rc;
+        if ((rc = launch_particle_mlp_dx(p->q1_inv.net, a.X_next, (long long)N * Dx, T, N, Dx, w.mu1i_all, st))) return rc;
+      }
+      a.mu_f = t >= 1 ? w.mu_f_all + (size_t)(t - 1) * N * Dx : w.mu_f;
+      a.mu1i = t <= T - 2 ? w.mu1i_all + (size_t)(t + 1) * N * Dx : w.mu1i;
+    } else {
+      if (t >= 1) if ((rc = launch_particle_mlp_dx(fd.net, Xs + (size_t)(t - 1) * N * Dx, (long long)T * N * Dx, B, N, Dx, w.mu_f, st))) return rc;
+      if (t <= T - 2) if ((rc = launch_particle_mlp_dx(p->q1_inv.net, a.X_next + (size_t)(t + 1) * N * Dx, (long long)T * N * Dx, B, N, Dx, w.mu1i, st))) return rc;
+    }
     rc = -1;
 #define PSVO_CASE_A(X, Y) if (DXP == X && DYP == Y) rc = launch_fb(ffbsi_bwd_cand_kernel<X, Y>, a, gridA, blockA, smemA, st);
     PSVO_CASE_A(4, 4) PSVO_CASE_A(4, 8) PSVO_CASE_A(4, 16) PSVO_CASE_A(4, 32)
