@@ -17,6 +17,7 @@
 // Afterwards the row-MLP reverse mode back-propagates the q2 / q0 / f(pre_x0) means to their parameters and
 // to pre_obs / pre_x0, and a tiny kernel maps the sigma statistics to d/d sigma_con.
 #include "mlp_bwd_tile.cuh"
+#include <algorithm>
 #include "smc_kernels.h"
 
 namespace psvo {
@@ -42,19 +43,23 @@ struct BwdArgs {
   float* gmu0;       // (B,Dx)
   float* gmuf0;      // (B,Dx)
   float* stats;      // [ST_SLOTS*2][32]
+  int t_all = 0;                  // bwd_emission only: 1 = ALL time steps in this launch (gXg is then (T,B,N,Dx)); it depends on forward outputs only
   unsigned int* gmax = nullptr;   // tensor-core path: max |ext_g| of the launch (bit pattern; mlp_bwd_tc's operand scale), or NULL
   int N, B, T, Dx, Dy, t;
   unsigned flags;
 };
 
-__device__ __forceinline__ float particle_weight_grad(const BwdArgs& a, int b, int n, bool live) {
+__device__ __forceinline__ float particle_weight_grad_at(const BwdArgs& a, int b, int n, int t, bool live) {
   // d L / d log_W_t[n]  (see file header)
   if (!live) return 0.0f;
   const bool resample = a.flags & PSVO_F_RESAMPLE;
-  const size_t bt = (size_t)b * a.T + (resample ? a.t : a.T - 1);
+  const size_t bt = (size_t)b * a.T + (resample ? t : a.T - 1);
   float g = expf(a.log_Ws[bt * a.N + n] - a.lse[bt]) * a.g_logZ_b[b];
-  if (a.g_log_Ws != nullptr) g += a.g_log_Ws[((size_t)b * a.T + a.t) * a.N + n];     // resampling mode only (checked by the ABI)
+  if (a.g_log_Ws != nullptr) g += a.g_log_Ws[((size_t)b * a.T + t) * a.N + n];     // resampling mode only (checked by the ABI)
   return g;
+}
+__device__ __forceinline__ float particle_weight_grad(const BwdArgs& a, int b, int n, bool live) {
+  return particle_weight_grad_at(a, b, n, a.t, live);
 }
 
 template <int DXP, int DYP>
@@ -78,16 +83,19 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
 
   const int tile = blockDim.x;
   const int tiles_per_seq = (N + tile - 1) / tile;
-  const int work = a.B * tiles_per_seq;
+  const int work_t = a.B * tiles_per_seq;
+  const int work = a.t_all ? work_t * a.T : work_t;          // t_all: every (t, b, tile) of the pass in one launch
   float st_sg[DYP];
 #pragma unroll
   for (int d = 0; d < DYP; ++d) st_sg[d] = 0.0f;
 
-  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+  for (int wj = blockIdx.x; wj < work; wj += gridDim.x) {
+    const int t = a.t_all ? wj / work_t : a.t;
+    const int wi = a.t_all ? wj - t * work_t : wj;
     const int b = wi / tiles_per_seq;
     const int n = (wi - b * tiles_per_seq) * tile + threadIdx.x;
     const bool live = n < N;
-    const size_t bt = (size_t)b * a.T + a.t;
+    const size_t bt = (size_t)b * a.T + t;
     float x[DXP];
 #pragma unroll
     for (int d = 0; d < DXP; ++d) x[d] = (live && d < Dx) ? a.Xs[(bt * N + n) * Dx + d] : 0.0f;
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
 #pragma unroll
     for (int d = 0; d < DXP; ++d) xx[0][d] = x[d];
     mlp_eval<DXP, DYP, 1>(gs, xx, mug, nullptr, 0);
-    const float gl = particle_weight_grad(a, b, n, live);
+    const float gl = particle_weight_grad_at(a, b, n, t, live);
     float G[DYP];
 #pragma unroll
     for (int d = 0; d < DYP; ++d) {
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(256) bwd_emission_kernel(BwdArgs a) {
     mlp_bwd_tile<DXP, DYP>(gs, gg, x, G, gx, stage);
     if (live) {
 #pragma unroll
-      for (int d = 0; d < DXP; ++d) if (d < Dx) a.gXg[((size_t)b * N + n) * Dx + d] = gx[d];
+      for (int d = 0; d < DXP; ++d) if (d < Dx) a.gXg[(((size_t)(a.t_all ? t : 0) * a.B + b) * N + n) * Dx + d] = gx[d];
     }
   }
   __syncthreads();
@@ -605,6 +613,7 @@ static size_t staged_floats(const psvo_mlp& net, int din_pad, int dout_pad) {
 
 struct BwdWs {
   float *sig, *mu2_all, *mu0, *muf0, *gmu2_all, *gmu0, *gmuf0, *gXa, *gXb, *gXg, *stats, *gx0tmp;
+  float* gXg_all;      // (T,B,N,Dx): emission contributions of all steps from ONE launch (small passes on the FP32 kernels), or NULL
   float *tc_mu, *tc_muq, *tc_g; unsigned char *img_g, *img_q1, *img_fwd; unsigned int* gmax;     // tensor-core reverse mode (or NULL)
   float *rows_x, *rows_gx;                                                                       // generic row-MLP reverse mode: deep networks (or NULL)
   size_t bytes;
@@ -632,6 +641,9 @@ static BwdWs carve_bwd(const psvo_dims* d, const psvo_params* p, char* base) {
   w.mu2_all = take(BT * d->Dx); w.mu0 = take((size_t)d->B * d->Dx); w.muf0 = take((size_t)d->B * d->Dx);
   w.gmu2_all = take(BT * d->Dx); w.gmu0 = take((size_t)d->B * d->Dx); w.gmuf0 = take((size_t)d->B * d->Dx);
   w.gXa = take(BN * d->Dx); w.gXb = take(BN * d->Dx); w.gXg = take(BN * d->Dx);
+  w.gXg_all = nullptr;
+  if (p != nullptr && !tc_backward_ok(d, p) && !deep_rows_backward(d, p) && (size_t)d->T * BN * d->Dx <= (size_t)1 << 22)
+    w.gXg_all = take((size_t)d->T * BN * d->Dx);
   w.stats = take(ST_SLOTS * 2 * 32);
   w.gx0tmp = take((size_t)d->B * d->Dx0);
   w.tc_mu = w.tc_muq = w.tc_g = nullptr; w.img_g = w.img_q1 = w.img_fwd = nullptr; w.gmax = nullptr;
@@ -857,13 +869,24 @@ PSVO_API int psvo_smc_backward(const psvo_dims* d, const psvo_params* p, const f
       float* tmp = gXin; gXin = gXout; gXout = tmp;
       continue;
     }
-    int rc = -1;
-#define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, grid_of(blkE, smE), smE, st);
-    PSVO_CASE_E(4, 4) PSVO_CASE_E(4, 8) PSVO_CASE_E(4, 16) PSVO_CASE_E(4, 32)
-    PSVO_CASE_E(8, 4) PSVO_CASE_E(8, 8) PSVO_CASE_E(8, 16) PSVO_CASE_E(8, 32)
-    PSVO_CASE_E(16, 4) PSVO_CASE_E(16, 8) PSVO_CASE_E(16, 16) PSVO_CASE_E(16, 32)
+    int rc = 0;
+    // small passes: the emission side depends on forward outputs only, so ONE launch covers all T steps (before the first step
+    // of this loop); the per-step proposal kernels then read their slice of it
+    const bool emis_all = w.gXg_all != nullptr;
+    if (!emis_all || t == T - 1) {
+      a.t_all = emis_all ? 1 : 0;
+      a.gXg = emis_all ? w.gXg_all : w.gXg;
+      const int gridE = emis_all ? (int)std::min<int64_t>((int64_t)grid_of(blkE, smE) * T, (int64_t)num_sms() * 4) : grid_of(blkE, smE);
+      rc = -1;
+#define PSVO_CASE_E(X, Y) if (DXP == X && DYP == Y) rc = launch_emission_t<X, Y>(a, blkE, gridE, smE, st);
+      PSVO_CASE_E(4, 4) PSVO_CASE_E(4, 8) PSVO_CASE_E(4, 16) PSVO_CASE_E(4, 32)
+      PSVO_CASE_E(8, 4) PSVO_CASE_E(8, 8) PSVO_CASE_E(8, 16) PSVO_CASE_E(8, 32)
+      PSVO_CASE_E(16, 4) PSVO_CASE_E(16, 8) PSVO_CASE_E(16, 16) PSVO_CASE_E(16, 32)
 #undef PSVO_CASE_E
-    if (rc) return rc;
+      if (rc) return rc;
+      a.t_all = 0;
+    }
+    if (emis_all) a.gXg = w.gXg_all + (size_t)t * BN * Dx;
     rc = DXP == 4 ? launch_proposal_t<4>(a, blkP, grid_of(blkP, smP), smP, st)
                   : (DXP == 8 ? launch_proposal_t<8>(a, blkP, grid_of(blkP, smP), smP, st)
                               : launch_proposal_t<16>(a, blkP, grid_of(blkP, smP), smP, st));
