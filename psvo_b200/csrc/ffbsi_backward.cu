@@ -52,6 +52,8 @@ struct FbArgs {
   const float* gin;          // (B,N,Dx) gradient arriving at the picked candidate of trajectory i
   float* gin_next;           // (B,N,Dx) produced by ffbsi_bwd_traj for step t+1
   float* candX; float* candK; float* candP;       // (B,N,M,DXP) | (B,N,M) | (B,N,M)
+  int pair_all = 0;          // ffbsi_bwd_pair_kernel only: 1 = the j side of ALL steps t = 1..T-1 in one launch (batch 1: candX / candK /
+                             // candP hold every step's candidates, mu_f points at the (T,N,Dx) means of all steps)
   float* gmu1i; float* gxn;  // (B,N,Dx)
   float* gm2_all; float* gmu_init_all; float* gmu0;
   float* g_Xs; float* g_log_Ws;
@@ -411,7 +413,7 @@ template <int DXP>
 __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
   griddep_entry();
   extern __shared__ __align__(16) float smem[];
-  const int Dx = a.Dx, N = a.N, M = a.M, T = a.T, t = a.t;
+  const int Dx = a.Dx, N = a.N, M = a.M, T = a.T;
   const bool boot = a.flags & PSVO_F_BOOTSTRAP;
   const int P = blockDim.x, tid = threadIdx.x;
   MlpS<DXP, DXP> fs;
@@ -435,26 +437,31 @@ __global__ void __launch_bounds__(256) ffbsi_bwd_pair_kernel(FbArgs a) {
   if (2 * N <= P) { NP2 = 1; while (NP2 < N) NP2 *= 2; S = P / NP2; }
   const int slice = tid / NP2;
   const int tiles_per_seq = S > 1 ? 1 : (N + P - 1) / P;
-  const int work = a.B * tiles_per_seq;
+  const int work_t = a.B * tiles_per_seq;
+  const int work = a.pair_all ? work_t * (T - 1) : work_t;
   const long long ncand = (long long)N * M;
-  for (int wi = blockIdx.x; wi < work; wi += gridDim.x) {
+  for (int wj = blockIdx.x; wj < work; wj += gridDim.x) {
+    const int t = a.pair_all ? 1 + wj / work_t : a.t;
+    const int wi = a.pair_all ? wj - (t - 1) * work_t : wj;
     const int b = wi / tiles_per_seq;
     const int j = S > 1 ? tid % NP2 : (wi - b * tiles_per_seq) * P + tid;
     const bool live = j < N;
     const size_t btm = (size_t)b * T + (t - 1);
+    const size_t step_off = a.pair_all ? (size_t)t * a.B * ncand : 0;               // this step's slice of the candidate buffers
+    const float* mu_f_t = a.pair_all ? a.mu_f + (size_t)(t - 1) * N * Dx : a.mu_f;  // (batch 1)
     float x[DXP], mus[DXP];
 #pragma unroll
     for (int d = 0; d < DXP; ++d) {
       x[d] = (live && d < Dx) ? a.Xs[(btm * N + j) * Dx + d] : 0.0f;
-      mus[d] = (live && d < Dx) ? a.mu_f[((size_t)b * N + j) * Dx + d] / sf[d] : 0.0f;
+      mus[d] = (live && d < Dx) ? mu_f_t[((size_t)b * N + j) * Dx + d] / sf[d] : 0.0f;
     }
     const float wb = live ? a.log_Ws[btm * N + j] - a.lse[btm] : -INFINITY;
     float Gj = 0.0f, Ksum = 0.0f, gm[DXP];
 #pragma unroll
     for (int d = 0; d < DXP; ++d) gm[d] = 0.0f;
-    const float* cX = a.candX + (size_t)b * ncand * DXP;
-    const float* cK = a.candK + (size_t)b * ncand;
-    const float* cP = a.candP + (size_t)b * ncand;
+    const float* cX = a.candX + (step_off + (size_t)b * ncand) * DXP;
+    const float* cK = a.candK + step_off + (size_t)b * ncand;
+    const float* cP = a.candP + step_off + (size_t)b * ncand;
     for (long long c0 = 0; c0 < ncand; c0 += kBwdPairChunk) {
       __syncthreads();
       const int nc = (int)min((long long)kBwdPairChunk, ncand - c0);
@@ -644,6 +651,7 @@ static int launch_fb(K kern, const FbArgs& a, int grid, int block, size_t smem, 
 }
 
 struct FbWs {
+  int cand_steps;                  // slices of candX / candK / candP (T when the pair kernel runs once per pass, else 1)
   float *mu_f_all, *mu1i_all;      // batch 1: the means of ALL time steps, two launches per pass instead of two per step (or NULL)
   float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *coef, *candX, *candK, *candP, *gmu1i, *gxn, *ginA, *ginB,
         *gm2_all, *gmu_init_all, *gmu0, *stats, *gfeat_tmp, *gx0_tmp;
@@ -662,7 +670,10 @@ static FbWs carve_fb(const psvo_dims* d, char* base) {
   w.mu1i_all = all_steps ? take((size_t)d->T * d->N * d->Dx) : nullptr;
   w.m2_all = take(BT * d->Dx); w.mu_init_all = take(BT * d->Dx); w.mu0i = take((size_t)d->B * d->Dx);
   w.coef = take(wr ? BT * d->N : BN);
-  w.candX = take(BNM * DXP); w.candK = take(BNM); w.candP = take(BNM);
+  // batch 1 with small candidate sets: one slice per time step, so that the j side of the pairwise term (it only feeds outputs
+  // and the f-network gradients) runs for ALL steps in one launch after the loop
+  w.cand_steps = (all_steps && (size_t)d->T * BNM * (DXP + 2) <= (size_t)1 << 23) ? d->T : 1;
+  w.candX = take(w.cand_steps * BNM * DXP); w.candK = take(w.cand_steps * BNM); w.candP = take(w.cand_steps * BNM);
   w.gmu1i = take(BN * d->Dx); w.gxn = take(BN * d->Dx); w.ginA = take(BN * d->Dx); w.ginB = take(BN * d->Dx);
   w.gm2_all = take(BT * d->Dx); w.gmu_init_all = take(BT * d->Dx); w.gmu0 = take((size_t)d->B * d->Dx);
   w.stats = take(FS_SLOTS * 32);
@@ -790,8 +801,11 @@ PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p, const
 
   float* gin = w.ginA;
   float* gin_next = w.ginB;
+  const bool pair_deferred = w.cand_steps == T && T > 1 && w.mu_f_all != nullptr;
+  const size_t BNM_ = BN * (size_t)M;
   for (int t = 0; t < T; ++t) {
     a.t = t; a.gin = gin; a.gin_next = gin_next;
+    if (pair_deferred) { a.candX = w.candX + (size_t)t * BNM_ * DXP; a.candK = w.candK + (size_t)t * BNM_; a.candP = w.candP + (size_t)t * BNM_; }
     int rc = 0;
     if (w.mu_f_all != nullptr) {
       // batch 1: both inputs (the filter's particles, the simulated trajectories) are known for every step: row (t, n) of the
@@ -813,7 +827,7 @@ PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p, const
     PSVO_CASE_A(16, 4) PSVO_CASE_A(16, 8) PSVO_CASE_A(16, 16) PSVO_CASE_A(16, 32)
 #undef PSVO_CASE_A
     if (rc) return rc;
-    if (t >= 1) {
+    if (t >= 1 && !pair_deferred) {
       rc = DXP == 4 ? launch_fb(ffbsi_bwd_pair_kernel<4>, a, grid_of(blockB), blockB, smemB, st)
                     : (DXP == 8 ? launch_fb(ffbsi_bwd_pair_kernel<8>, a, grid_of(blockB), blockB, smemB, st)
                                 : launch_fb(ffbsi_bwd_pair_kernel<16>, a, grid_of(blockB), blockB, smemB, st));
@@ -827,6 +841,16 @@ PSVO_API int psvo_ffbsi_backward(const psvo_dims* d, const psvo_params* p, const
       if (rc) return rc;
     }
     float* tmp = gin; gin = gin_next; gin_next = tmp;
+  }
+  if (pair_deferred && T >= 2) {
+    a.pair_all = 1; a.candX = w.candX; a.candK = w.candK; a.candP = w.candP; a.mu_f = w.mu_f_all;
+    const long long gB = (long long)grid_of(blockB) * (T - 1);
+    const int gridB = (int)(gB < 4LL * num_sms() ? gB : 4LL * num_sms());
+    const int rc = DXP == 4 ? launch_fb(ffbsi_bwd_pair_kernel<4>, a, gridB, blockB, smemB, st)
+                            : (DXP == 8 ? launch_fb(ffbsi_bwd_pair_kernel<8>, a, gridB, blockB, smemB, st)
+                                        : launch_fb(ffbsi_bwd_pair_kernel<16>, a, gridB, blockB, smemB, st));
+    if (rc) return rc;
+    a.pair_all = 0;
   }
 
   // per-sequence networks: BSim_q2 and BSim_q_init over (b,t) rows, the initial density's network over b rows
