@@ -461,7 +461,7 @@ static int launch_step_t(const FfbsiArgs& a, int block, int grid, size_t smem, c
   return 0;
 }
 
-struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG, *candQ; unsigned char *bimg, *tc_image, *tc_image2; size_t bytes; };
+struct FfWs { float *mu_f_all; float *sig, *mu_f, *mu1i, *m2_all, *mu_init_all, *mu0i, *omega_pick, *candP, *candF, *candG, *candQ; unsigned char *bimg, *tc_image, *tc_image2; int bimg_steps; size_t bytes; };
 static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   FfWs w; size_t off = 0;
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(base + off); off += align_up(floats * sizeof(float), 256); return r; };
@@ -473,10 +473,13 @@ static FfWs carve_ff(const psvo_dims* d, const psvo_params* p, char* base) {
   w.mu_f_all = (d->B == 1 && (size_t)d->T * d->N * d->Dx <= (size_t)1 << 26) ? take((size_t)d->T * d->N * d->Dx) : nullptr;
   w.m2_all = take(BT * d->Dx); w.mu_init_all = take(BT * d->Dx); w.mu0i = take((size_t)d->B * d->Dx);
   w.omega_pick = take(BT * d->N);
-  w.candP = nullptr; w.bimg = nullptr;
+  w.candP = nullptr; w.bimg = nullptr; w.bimg_steps = 1;
   if (ffbsi_pair_tc_supported(d->N, d->M, d->B, d->Dx)) {
     w.candP = take(BN * d->M);
-    w.bimg = reinterpret_cast<unsigned char*>(take(ffbsi_pair_tc_image_bytes(d->B, d->N) / sizeof(float)));
+    // batch 1: one B image per time step (they depend on forward outputs only), prepared by ONE launch before the loop
+    const size_t ib = ffbsi_pair_tc_image_bytes(d->B, d->N);
+    w.bimg_steps = (w.mu_f_all != nullptr && d->T >= 2 && d->T <= 65536 && (size_t)d->T * ib <= (size_t)64 << 20) ? d->T : 1;
+    w.bimg = reinterpret_cast<unsigned char*>(take((size_t)w.bimg_steps * ib / sizeof(float)));
   }
   w.candF = w.candG = w.candQ = nullptr; w.tc_image = w.tc_image2 = nullptr;
   if (p != nullptr) {
@@ -619,6 +622,11 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
 #undef PSVO_CASE_FL
     if (rc) return rc;
   }
+  if (pair_tc && w.bimg_steps > 1) {
+    PairTcArgs pa = pt;
+    pa.bimg = w.bimg; pa.mu_f = w.mu_f_all;
+    if (int e = launch_ffbsi_pair_prep_all(pa, st)) return e;
+  }
   for (int t = whole_pass ? -1 : T - 1; t >= 0; --t) {
     a.t = t;
     int rc = 0;
@@ -655,6 +663,7 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
     a.P_ext = nullptr;
     if (pair_tc && t >= 1) {
       pt.t = t;
+      if (w.bimg_steps > 1) { pt.bimg = w.bimg + (size_t)t * ffbsi_pair_tc_image_bytes(B, N); pt.prep_done = 1; }
       if ((rc = launch_ffbsi_pair_tc(pt, st))) return rc;
       a.P_ext = w.candP;
     }

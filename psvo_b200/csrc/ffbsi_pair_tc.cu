@@ -49,19 +49,21 @@ __global__ void __launch_bounds__(128) ffbsi_pair_prep_kernel(PairTcArgs a) {
   const int ct = j / kPtCols, r = j - ct * kPtCols;
   if (ct >= NT) return;
   const bool live = j < N;
-  const size_t btm = (size_t)b * a.T + (a.t - 1);
+  const int t = a.prep_all ? 1 + (int)blockIdx.z : a.t;                       // prep_all: grid.z walks the steps 1..T-1 (batch 1)
+  const size_t btm = (size_t)b * a.T + (t - 1);
+  const float* mu_f_t = a.prep_all ? a.mu_f + (size_t)(t - 1) * N * Dx : a.mu_f;
   float mus[16];
   float nrm = 0.0f;
 #pragma unroll
   for (int d = 0; d < 16; ++d) {
     float v = 0.0f;
-    if (live && d < Dx) v = a.mu_f[((size_t)b * N + j) * Dx + d] / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
+    if (live && d < Dx) v = mu_f_t[((size_t)b * N + j) * Dx + d] / a.sig[(boot ? SIG_Q1 : SIG_F) * 32 + d];
     mus[d] = v;
     nrm = fmaf(v, v, nrm);
   }
   float cj = kPtSentinel;
   if (live) cj = fmaxf((a.log_Ws[btm * N + j] - a.lse[btm]) - 0.5f * nrm, kPtSentinel);
-  unsigned char* img = a.bimg + ((size_t)b * NT + ct) * kPtTileBytes;
+  unsigned char* img = a.bimg + (a.prep_all ? (size_t)t * a.B * NT * kPtTileBytes : 0) + ((size_t)b * NT + ct) * kPtTileBytes;
 #pragma unroll
   for (int kg = 0; kg < 2; ++kg) {
     float v[8];
@@ -338,8 +340,17 @@ bool ffbsi_pair_tc_supported(int N, int M, int B, int Dx) {
 
 size_t ffbsi_pair_tc_image_bytes(int B, int N) { return (size_t)B * ((N + kPtCols - 1) / kPtCols) * kPtTileBytes; }
 
+int launch_ffbsi_pair_prep_all(PairTcArgs a, cudaStream_t st) {
+  PSVO_REQUIRE(a.T >= 2 && a.T - 1 <= 65535, "pairwise B images of all steps: T out of range");
+  a.prep_all = 1;
+  ProfScope ps_(PK_FFBSI, st);
+  PSVO_CUDA(launch_pdl(ffbsi_pair_prep_kernel, dim3((a.N + 127) / 128, a.B, a.T - 1), dim3(128), 0, st, pdl_enabled(), a));
+  PSVO_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st) {
-  {
+  if (!a.prep_done) {
     ProfScope ps_(PK_FFBSI, st);
     PSVO_CUDA(launch_pdl(ffbsi_pair_prep_kernel, dim3((a.N + 127) / 128, a.B), dim3(128), 0, st, pdl_enabled(), a));
     PSVO_LAUNCH_CHECK();

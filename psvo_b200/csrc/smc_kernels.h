@@ -82,6 +82,9 @@ struct PairTcArgs {
   const float* sig; const float* mu_f; const float* mu1i; const float* m2_all; const float* mu_init_all;
   const float* log_Ws; const float* lse; const float* eps_bw;
   unsigned char* bimg;     // B image workspace, ffbsi_pair_tc_image_bytes()
+  int prep_all = 0;        // prep kernel only: 1 = the B images of ALL steps t = 1..T-1 in one launch (batch 1: bimg holds T slices,
+                           // mu_f points at the (T,N,Dx) means of all steps)
+  int prep_done = 0;       // launch_ffbsi_pair_tc: the B image of this step is already in bimg
   float* candP;            // (B, N, M) out: LSE_j( -|x~/s - mu_j/s|^2 / 2 + log Wbar_j )
   unsigned long long seed;
   int N, M, B, T, Dx, t, seq_offset;
@@ -90,6 +93,7 @@ struct PairTcArgs {
 bool ffbsi_pair_tc_supported(int N, int M, int B, int Dx);
 size_t ffbsi_pair_tc_image_bytes(int B, int N);
 int launch_ffbsi_pair_tc(const PairTcArgs& a, cudaStream_t st);
+int launch_ffbsi_pair_prep_all(PairTcArgs a, cudaStream_t st);     // a.bimg: T slices, a.mu_f: (T,N,Dx)
 
 // tensor-core (tcgen05) propagate step (smc_propagate_tc.cu)
 bool tc_propagate_supported(const PropArgs& a);
