@@ -583,6 +583,14 @@ PSVO_API int psvo_ffbsi_forward(const psvo_dims* d, const psvo_params* p, const 
   const int DXP = pad_dx(Dx), DYP = pad_dy(d->Dy);
   int IL = 256 / M; if (IL < 1) IL = 1;
   if (IL > N) IL = N;
+  // few tiles (small batches): one warp per CTA on as many SMs as there are tiles beats eight warps sharing one SM and its
+  // barriers -- the step is a dependent chain per warp (config 2: 12.4 -> 12.1 ms per pass on the same box).  Per-trajectory
+  // arithmetic does not depend on the tile shape.  PSVO_FFBSI_IL caps the trajectories per tile by hand.
+  while (IL * M > 32 && IL % 2 == 0 && (int64_t)B * ((N + IL - 1) / IL) < num_sms()) IL /= 2;
+  {
+    static const int il_env = getenv("PSVO_FFBSI_IL") ? atoi(getenv("PSVO_FFBSI_IL")) : 0;
+    if (il_env > 0 && il_env <= N && il_env * M <= 256) IL = il_env;
+  }
   int block = ((IL * M + 31) / 32) * 32;
   a.IL = IL;
   // PSVO on the FP32 step kernel: MLP q1_inv of the picked particle (the next step's proposal mean) is evaluated by the step
